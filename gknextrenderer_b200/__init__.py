@@ -1,0 +1,251 @@
+"""gknextrenderer_b200 — B200 (sm_100a) CUDA backend for gkNextRenderer's path-tracing hot path.
+
+Layers:
+  csrc/   hand-written CUDA kernels + the C ABI of include/gknext_cuda.h  -> lib/libgknext_cuda.so
+  host/   C++ mirror of the reference's Assets::* / engine / LogicRendererBase interface,
+          driving the C ABI the way the reference's host code would      -> lib/libgknext_host.so
+  this package: thin ctypes wrappers used by tests/, bench.py and __graft_entry__.py.
+
+Nothing here computes on the CPU: every render / intersect call goes through the C ABI into
+CUDA kernels and fails loudly when the extension or a GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import GkUniformBufferObject, GkNodeProxy, GkSceneDesc, GkFrameStats, GkBvhInfo, GkConfig, GkRayCastResult, PLANES  # noqa: F401
+
+__all__ = ["Engine", "Renderer", "GkError", "PLANES", "plane_dtype"]
+
+
+class GkError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"[gk status {status}] {message}")
+        self.status = status
+
+
+_cuda = None
+_host = None
+
+
+def cuda_lib():
+    global _cuda
+    if _cuda is None:
+        _cuda = N.load_cuda()
+    return _cuda
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        _host = N.load_host()
+    return _host
+
+
+def plane_dtype(name: str):
+    """(numpy dtype, channels) of a plane as gk_readback returns it."""
+    if name in ("OBJECT_ID0", "OBJECT_ID1", "RAY_COUNT"):
+        return np.uint32, 1
+    if name in ("DEPTH", "PRIMARY_T"):
+        return np.float32, 1
+    if name == "MOTION":
+        return np.float32, 2
+    if name == "PRIMARY_IDS":
+        return np.uint32, 2
+    if name in ("RADIANCE_DIFFUSE_F32", "RADIANCE_SPECULAR_F32"):
+        return np.float32, 4
+    return np.float16, 4
+
+
+class Engine:
+    """Host mirror: scene (Assets::Scene), user settings and per-frame UBO (NextEngine)."""
+
+    def __init__(self, scene: str = "cornell", p0: int = 0, p1: int = 0, p2: int = 0, p3: int = 0):
+        self.lib = host_lib()
+        self.h = self.lib.gkh_engine_create(scene.encode(), p0, p1, p2, p3)
+        if not self.h:
+            raise GkError(-1, self.lib.gkh_last_error().decode())
+        self.scene_name = scene
+
+    def close(self):
+        if self.h:
+            self.lib.gkh_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, **settings):
+        for k, v in settings.items():
+            if self.lib.gkh_set_setting(self.h, k.encode(), float(v)) != 0:
+                raise GkError(-1, self.lib.gkh_last_error().decode())
+        return self
+
+    def look_at(self, eye, center, up=(0, 1, 0), fov=40.0):
+        a = (C.c_float * 3)(*eye)
+        b = (C.c_float * 3)(*center)
+        c = (C.c_float * 3)(*up)
+        self.lib.gkh_set_camera_lookat(self.h, a, b, c, float(fov))
+
+    def scene_desc(self):
+        return self.lib.gkh_scene_desc(self.h)
+
+    def triangles(self, instanced=False) -> int:
+        return int(self.lib.gkh_scene_triangles(self.h, 1 if instanced else 0))
+
+    def update_nodes(self):
+        """Scene::UpdateNodes — returns (pointer to NodeProxy[], count)."""
+        n = self.lib.gkh_update_nodes(self.h)
+        return self.lib.gkh_node_proxies(self.h), int(n)
+
+    def mark_dirty(self):
+        self.lib.gkh_mark_dirty(self.h)
+
+    def step_scene(self, frame: int):
+        self.lib.gkh_scene_step(self.h, frame)
+
+    def set_node_translation(self, node, x, y, z):
+        self.lib.gkh_set_node_translation(self.h, node, x, y, z)
+
+    def ubo(self, width, height) -> GkUniformBufferObject:
+        u = GkUniformBufferObject()
+        self.lib.gkh_get_ubo(self.h, width, height, C.byref(u))
+        return u
+
+    def advance_frame(self):
+        self.lib.gkh_advance_frame(self.h)
+
+    def screen_ray(self, x, y, width, height):
+        o = (C.c_float * 3)()
+        d = (C.c_float * 3)()
+        self.lib.gkh_screen_ray(self.h, x, y, width, height, o, d)
+        return np.array(o[:], np.float32), np.array(d[:], np.float32)
+
+
+class Renderer:
+    """One GkContext: the CUDA path tracer behind the C ABI."""
+
+    def __init__(self, width, height, device=-1, tile_index=0, tile_count=1, tile_rows=16):
+        self.lib = cuda_lib()
+        cfg = GkConfig()
+        cfg.device, cfg.width, cfg.height = device, width, height
+        cfg.tileIndex, cfg.tileCount, cfg.tileRows = tile_index, tile_count, tile_rows
+        h = C.c_void_p()
+        self._check(self.lib.gk_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.width, self.height = width, height
+
+    def _check(self, status):
+        if status != N.GK_OK:
+            raise GkError(status, self.lib.gk_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- scene ---
+    def upload_scene(self, desc):
+        self._check(self.lib.gk_upload_scene(self.h, desc))
+
+    def update_instances(self, nodes, count, refit=False):
+        self._check(self.lib.gk_update_instances(self.h, nodes, count, 1 if refit else 0))
+
+    def load(self, engine: Engine, refit=False):
+        self.upload_scene(engine.scene_desc())
+        nodes, n = engine.update_nodes()
+        self.update_instances(nodes, n, refit)
+
+    def set_ubo(self, ubo):
+        self._check(self.lib.gk_set_ubo(self.h, C.byref(ubo)))
+
+    # --- frames ---
+    def render_frame(self):
+        self._check(self.lib.gk_render_frame(self.h))
+
+    def trace_frame(self):
+        self._check(self.lib.gk_trace_frame(self.h))
+
+    def filter_frame(self):
+        self._check(self.lib.gk_filter_frame(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.gk_synchronize(self.h))
+
+    def stats(self) -> GkFrameStats:
+        s = GkFrameStats()
+        self._check(self.lib.gk_get_stats(self.h, C.byref(s)))
+        return s
+
+    def bvh_info(self) -> GkBvhInfo:
+        s = GkBvhInfo()
+        self._check(self.lib.gk_get_bvh_info(self.h, C.byref(s)))
+        return s
+
+    def set_traversal_stats(self, on: bool):
+        self._check(self.lib.gk_set_traversal_stats(self.h, 1 if on else 0))
+
+    # --- planes ---
+    def plane_bytes(self, name):
+        return int(self.lib.gk_plane_bytes(self.h, PLANES[name]))
+
+    def readback(self, name, out: np.ndarray | None = None) -> np.ndarray:
+        dt, ch = plane_dtype(name)
+        shape = (self.height, self.width, ch) if ch > 1 else (self.height, self.width)
+        if out is None:
+            out = np.empty(shape, dt)
+        assert out.nbytes == self.plane_bytes(name), (out.nbytes, self.plane_bytes(name))
+        self._check(self.lib.gk_readback(self.h, PLANES[name], out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def upload_plane(self, name, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes == self.plane_bytes(name), (arr.nbytes, self.plane_bytes(name))
+        self._check(self.lib.gk_upload_plane(self.h, PLANES[name], arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def plane_device_ptr(self, name) -> int:
+        return int(self.lib.gk_plane_device(self.h, PLANES[name]) or 0)
+
+    def stream(self) -> int:
+        return int(self.lib.gk_stream(self.h) or 0)
+
+    # --- queries ---
+    def intersect(self, rays: np.ndarray):
+        """rays: (n, 8) float32 {O.xyz, tmin, D.xyz, tmax} -> (tuv (n,3) f32, ids (n,2) u32)."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        tuv = np.empty((n, 3), np.float32)
+        ids = np.empty((n, 2), np.uint32)
+        self._check(self.lib.gk_intersect(self.h, rays.ctypes.data_as(C.c_void_p), n, tuv.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p)))
+        return tuv, ids
+
+    def intersect_device(self, d_rays: int, n: int, d_tuv: int, d_ids: int, any_hit=False):
+        self._check(self.lib.gk_intersect_device(self.h, C.c_void_p(d_rays), n, C.c_void_p(d_tuv), C.c_void_p(d_ids), 1 if any_hit else 0))
+
+    def raycast(self, origin_dir: np.ndarray):
+        od = np.ascontiguousarray(origin_dir, np.float32)
+        n = od.shape[0]
+        out = (GkRayCastResult * n)()
+        self._check(self.lib.gk_raycast(self.h, od.ctypes.data_as(C.c_void_p), n, out))
+        return out
+
+    def set_ray_capture(self, wave: int):
+        self._check(self.lib.gk_set_ray_capture(self.h, wave))
+
+    def captured_rays(self, capacity: int) -> np.ndarray:
+        buf = np.empty((capacity, 8), np.float32)
+        cnt = C.c_uint32()
+        self._check(self.lib.gk_get_captured_rays(self.h, buf.ctypes.data_as(C.c_void_p), capacity, C.byref(cnt)))
+        return buf[: min(capacity, cnt.value)]

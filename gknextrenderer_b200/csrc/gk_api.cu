@@ -1,0 +1,432 @@
+// gk_api.cu — the extern "C" entry points declared in include/gknext_cuda.h.
+// Each function's header comment there cites the reference interface it replaces.
+#include "gk_context.h"
+#include <cstring>
+#include <new>
+
+namespace gk {
+
+static thread_local std::string g_lastError;
+void setLastError(const std::string& s) { g_lastError = s; }
+
+__global__ void k_pack_rays(const float* __restrict__ originDir, uint32_t n, float4* rays)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rays[2 * i] = make_float4(originDir[6 * i], originDir[6 * i + 1], originDir[6 * i + 2], 0.0f);
+    rays[2 * i + 1] = make_float4(originDir[6 * i + 3], originDir[6 * i + 4], originDir[6 * i + 5], kPrimaryTMax);
+}
+
+// RayCastInCPU's result record (CPUAccelerationStructure.cpp:283-307) from a closest hit
+__global__ void k_raycast_results(const float* __restrict__ originDir, const float* __restrict__ tuv, const uint32_t* __restrict__ ids, uint32_t n,
+                                  const GkNodeProxy* __restrict__ nodes, const ModelInfo* __restrict__ models, const float4* __restrict__ faceNormals,
+                                  GkRayCastResult* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GkRayCastResult R;
+    memset(&R, 0, sizeof(R));
+    const uint32_t node = ids[2 * i + 1], prim = ids[2 * i];
+    if (node != kInvalid) {
+        const float t = tuv[3 * i];
+        const GkNodeProxy& p = nodes[node];
+        const float4 fn = faceNormals[models[p.modelId / 10].triOffset + prim];
+        R.HitPoint[0] = originDir[6 * i] + originDir[6 * i + 3] * t;
+        R.HitPoint[1] = originDir[6 * i + 1] + originDir[6 * i + 4] * t;
+        R.HitPoint[2] = originDir[6 * i + 2] + originDir[6 * i + 5] * t;
+        const float* W = p.worldTS;
+        R.Normal[0] = (W[0] * fn.x + W[4] * fn.y) + (W[8] * fn.z + W[12] * 0.0f);
+        R.Normal[1] = (W[1] * fn.x + W[5] * fn.y) + (W[9] * fn.z + W[13] * 0.0f);
+        R.Normal[2] = (W[2] * fn.x + W[6] * fn.y) + (W[10] * fn.z + W[14] * 0.0f);
+        R.Normal[3] = (W[3] * fn.x + W[7] * fn.y) + (W[11] * fn.z + W[15] * 0.0f);
+        R.T = t;
+        R.InstanceId = p.instanceId;
+        R.Hitted = 1;
+    }
+    out[i] = R;
+}
+
+static GkStatus selectDevice(Context& c)
+{
+    GK_CUDA(cudaSetDevice(c.device));
+    return GK_OK;
+}
+
+static GkPlane resolvePlane(const Context& c, GkPlane plane)
+{
+    // after a frame the reference's history images hold copies of the accumulated ones
+    if (!c.pendingHistorySwap) return plane;
+    switch (plane) {
+    case GK_PLANE_HISTORY_DIFFUSE: return GK_PLANE_ACCUM_DIFFUSE;
+    case GK_PLANE_HISTORY_SPECULAR: return GK_PLANE_ACCUM_SPECULAR;
+    case GK_PLANE_HISTORY_ALBEDO: return GK_PLANE_ACCUM_ALBEDO;
+    case GK_PLANE_OBJECT_ID1: return GK_PLANE_OBJECT_ID0;
+    default: return plane;
+    }
+}
+
+} // namespace gk
+
+using namespace gk;
+
+#define GK_CHECK_CTX(ctx)                                  \
+    if (!(ctx)) {                                          \
+        gk::setLastError("null context");                  \
+        return GK_ERR_INVALID_ARGUMENT;                    \
+    }                                                      \
+    Context& c = (ctx)->c;                                 \
+    {                                                      \
+        GkStatus _s = selectDevice(c);                     \
+        if (_s != GK_OK) return _s;                        \
+    }
+
+extern "C" {
+
+int gk_abi_version(void) { return GK_ABI_VERSION; }
+const char* gk_last_error(void) { return g_lastError.c_str(); }
+
+GkStatus gk_create(const GkConfig* cfg, GkContext** out)
+{
+    if (!cfg || !out || cfg->width == 0 || cfg->height == 0) {
+        setLastError("gk_create: bad configuration");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        setLastError(std::string("gk_create: no CUDA device (") + cudaGetErrorString(e) + "); this backend has no CPU fallback");
+        return GK_ERR_CUDA;
+    }
+    int dev = cfg->device;
+    if (dev < 0) GK_CUDA(cudaGetDevice(&dev));
+    if (dev >= count) {
+        setLastError("gk_create: device ordinal out of range");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    cudaDeviceProp prop;
+    GK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        setLastError(std::string("gk_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                     "; this library carries sm_100a code only");
+        return GK_ERR_UNSUPPORTED;
+    }
+    GkContext* h = new (std::nothrow) GkContext();
+    if (!h) return GK_ERR_OUT_OF_MEMORY;
+    Context& c = h->c;
+    c.device = dev;
+    c.width = cfg->width, c.height = cfg->height;
+    c.tileCount = cfg->tileCount ? cfg->tileCount : 1;
+    c.tileIndex = cfg->tileIndex;
+    c.tileRows = cfg->tileRows ? cfg->tileRows : 16;
+    c.flags = cfg->flags;
+    if (c.tileIndex >= c.tileCount) {
+        delete h;
+        setLastError("gk_create: tileIndex >= tileCount");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    GK_CUDA(cudaSetDevice(dev));
+    GK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    GkStatus s = allocFrameResources(c);
+    if (s != GK_OK) {
+        gk_destroy(h);
+        return s;
+    }
+    *out = h;
+    return GK_OK;
+}
+
+void gk_destroy(GkContext* ctx)
+{
+    if (!ctx) return;
+    Context& c = ctx->c;
+    cudaSetDevice(c.device);
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    freeFrameResources(c);
+    c.blasTree.release(), c.tlasTree.release();
+    c.dModels.release(), c.dGpuVerts.release(), c.dIndices.release(), c.dMaterials.release(), c.dLights.release(), c.dFaceNormals.release();
+    c.dNodes.release(), c.dCubes.release(), c.dVoxels.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dInst.release();
+    c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release();
+    c.dCapture.release();
+    for (cudaEvent_t e : c.evPool) cudaEventDestroy(e);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    delete ctx;
+}
+
+GkStatus gk_resize(GkContext* ctx, uint32_t width, uint32_t height)
+{
+    GK_CHECK_CTX(ctx);
+    if (width == 0 || height == 0) {
+        setLastError("gk_resize: empty extent");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    c.width = width, c.height = height;
+    c.pendingHistorySwap = false;
+    return allocFrameResources(c);
+}
+
+GkStatus gk_upload_scene(GkContext* ctx, const GkSceneDesc* scene)
+{
+    GK_CHECK_CTX(ctx);
+    if (!scene) {
+        setLastError("gk_upload_scene: null scene");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    return uploadScene(c, *scene);
+}
+
+GkStatus gk_update_materials(GkContext* ctx, const GkMaterial* materials, uint32_t count)
+{
+    GK_CHECK_CTX(ctx);
+    if (!materials || count == 0) {
+        setLastError("gk_update_materials: empty material list");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    GK_CUDA(c.dMaterials.reserve(count));
+    GK_CUDA(cudaMemcpyAsync(c.dMaterials.p, materials, sizeof(GkMaterial) * count, cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    c.materialCount = count;
+    return GK_OK;
+}
+
+GkStatus gk_update_instances(GkContext* ctx, const GkNodeProxy* nodes, uint32_t count, int refit)
+{
+    GK_CHECK_CTX(ctx);
+    return updateInstances(c, nodes, count, refit != 0);
+}
+
+GkStatus gk_set_probes(GkContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels, size_t count)
+{
+    GK_CHECK_CTX(ctx);
+    if (!cubes || !voxels || count == 0) {
+        c.haveProbes = false;
+        return GK_OK;
+    }
+    if (count != (size_t)GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z) {
+        setLastError("gk_set_probes: the probe grid is 192 x 48 x 192");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    GK_CUDA(c.dCubes.reserve(count));
+    GK_CUDA(c.dVoxels.reserve(count));
+    GK_CUDA(cudaMemcpyAsync(c.dCubes.p, cubes, sizeof(GkAmbientCube) * count, cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaMemcpyAsync(c.dVoxels.p, voxels, sizeof(GkVoxelData) * count, cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    c.haveProbes = true;
+    return GK_OK;
+}
+
+GkStatus gk_set_ubo(GkContext* ctx, const GkUniformBufferObject* ubo)
+{
+    GK_CHECK_CTX(ctx);
+    if (!ubo) {
+        setLastError("gk_set_ubo: null UBO");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    if (ubo->NumberOfSamples > 65535u || ubo->NumberOfBounces > 127u || ubo->MaxNumberOfBounces > 127u) {
+        setLastError("gk_set_ubo: samples <= 65535 and bounces <= 127 are supported");
+        return GK_ERR_UNSUPPORTED;
+    }
+    c.ubo = *ubo;
+    c.haveUbo = true;
+    return GK_OK;
+}
+
+GkStatus gk_trace_frame(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    return traceFrame(c);
+}
+
+GkStatus gk_filter_frame(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    return filterFrame(c);
+}
+
+GkStatus gk_render_frame(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    GkStatus s = traceFrame(c);
+    if (s != GK_OK) return s;
+    const float traceMs = c.stats.msTotal;
+    s = filterFrame(c);
+    c.stats.msTotal = traceMs + c.stats.msReproject + c.stats.msDenoise;
+    c.frameIndex++;
+    return s;
+}
+
+GkStatus gk_intersect_device(GkContext* ctx, const void* d_rays, uint32_t count, void* d_out_tuv, void* d_out_ids, int anyHit)
+{
+    GK_CHECK_CTX(ctx);
+    return intersectDevice(c, (const float4*)d_rays, count, (float*)d_out_tuv, (uint32_t*)d_out_ids, anyHit != 0);
+}
+
+GkStatus gk_intersect(GkContext* ctx, const float* rays, uint32_t count, float* out_tuv, uint32_t* out_ids)
+{
+    GK_CHECK_CTX(ctx);
+    if (count == 0) return GK_OK;
+    if (!rays) {
+        setLastError("gk_intersect: null rays");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    DevBuf<float4> dr;
+    DevBuf<float> dt;
+    DevBuf<uint32_t> di;
+    GK_CUDA(dr.reserve(2 * (size_t)count));
+    GK_CUDA(dt.reserve(3 * (size_t)count));
+    GK_CUDA(di.reserve(2 * (size_t)count));
+    GK_CUDA(cudaMemcpyAsync(dr.p, rays, 32 * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+    GkStatus s = intersectDevice(c, dr.p, count, dt.p, di.p, false);
+    if (s == GK_OK) {
+        if (out_tuv) GK_CUDA(cudaMemcpyAsync(out_tuv, dt.p, 12 * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
+        if (out_ids) GK_CUDA(cudaMemcpyAsync(out_ids, di.p, 8 * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
+        GK_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    dr.release(), dt.release(), di.release();
+    return s;
+}
+
+GkStatus gk_raycast(GkContext* ctx, const float* origin_dir, uint32_t count, GkRayCastResult* out)
+{
+    GK_CHECK_CTX(ctx);
+    if (count == 0) return GK_OK;
+    if (!origin_dir || !out) {
+        setLastError("gk_raycast: null argument");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    if (!c.haveScene || !c.haveInstances) {
+        setLastError("gk_raycast: scene and instances must be set first");
+        return GK_ERR_NOT_READY;
+    }
+    DevBuf<float> dod, dt;
+    DevBuf<float4> dr;
+    DevBuf<uint32_t> di;
+    DevBuf<GkRayCastResult> dres;
+    GK_CUDA(dod.reserve(6 * (size_t)count));
+    GK_CUDA(dr.reserve(2 * (size_t)count));
+    GK_CUDA(dt.reserve(3 * (size_t)count));
+    GK_CUDA(di.reserve(2 * (size_t)count));
+    GK_CUDA(dres.reserve(count));
+    GK_CUDA(cudaMemcpyAsync(dod.p, origin_dir, 24 * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+    k_pack_rays<<<(count + 255) / 256, 256, 0, c.stream>>>(dod.p, count, dr.p);
+    GkStatus s = intersectDevice(c, dr.p, count, dt.p, di.p, false);
+    if (s == GK_OK) {
+        k_raycast_results<<<(count + 255) / 256, 256, 0, c.stream>>>(dod.p, dt.p, di.p, count, c.dNodes.p, c.dModels.p, c.dFaceNormals.p, dres.p);
+        GK_CUDA(cudaGetLastError());
+        GK_CUDA(cudaMemcpyAsync(out, dres.p, sizeof(GkRayCastResult) * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
+        GK_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    dod.release(), dr.release(), dt.release(), di.release(), dres.release();
+    return s;
+}
+
+size_t gk_plane_bytes(const GkContext* ctx, GkPlane plane)
+{
+    if (!ctx || plane < 0 || plane >= GK_PLANE_COUNT) return 0;
+    return ctx->c.planes.bytes[plane];
+}
+
+GkStatus gk_readback(GkContext* ctx, GkPlane plane, void* dst, size_t bytes)
+{
+    GK_CHECK_CTX(ctx);
+    if (plane < 0 || plane >= GK_PLANE_COUNT || !dst || bytes != c.planes.bytes[plane]) {
+        setLastError("gk_readback: bad plane or size");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    GK_CUDA(cudaMemcpyAsync(dst, c.planes.p[resolvePlane(c, plane)], bytes, cudaMemcpyDeviceToHost, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return GK_OK;
+}
+
+GkStatus gk_upload_plane(GkContext* ctx, GkPlane plane, const void* src, size_t bytes)
+{
+    GK_CHECK_CTX(ctx);
+    if (plane < 0 || plane >= GK_PLANE_COUNT || !src || bytes != c.planes.bytes[plane]) {
+        setLastError("gk_upload_plane: bad plane or size");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    applyPendingHistorySwap(c);
+    GK_CUDA(cudaMemcpyAsync(c.planes.p[plane], src, bytes, cudaMemcpyHostToDevice, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return GK_OK;
+}
+
+void* gk_plane_device(GkContext* ctx, GkPlane plane)
+{
+    if (!ctx || plane < 0 || plane >= GK_PLANE_COUNT) return nullptr;
+    return ctx->c.planes.p[resolvePlane(ctx->c, plane)];
+}
+
+GkStatus gk_synchronize(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return GK_OK;
+}
+
+GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out)
+{
+    GK_CHECK_CTX(ctx);
+    if (!out) return GK_ERR_INVALID_ARGUMENT;
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.travStats) {
+        TraversalStats h;
+        GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));
+        c.stats.nodeVisits = h.nodeVisits, c.stats.triTests = h.triTests;
+    }
+    *out = c.stats;
+    return GK_OK;
+}
+
+GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out)
+{
+    GK_CHECK_CTX(ctx);
+    if (!out) return GK_ERR_INVALID_ARGUMENT;
+    memset(out, 0, sizeof(*out));
+    out->blasCount = (uint32_t)c.models.size();
+    out->instanceCount = c.nodeCount;
+    out->triangleCount = c.totalTris;
+    out->instancedTriangles = c.instancedTris;
+    out->blasNodes2 = c.blasTree.n ? c.blasTree.n - 1 : 0;
+    out->blasNodes8 = c.blasNodeCount;
+    out->tlasNodes2 = c.tlasTree.n ? c.tlasTree.n - 1 : 0;
+    out->tlasNodes8 = c.tlasNodeCount;
+    out->bytesGeometry = c.totalTris * sizeof(TriRecord) + c.dGpuVerts.bytes() + c.dIndices.bytes();
+    out->bytesBvh = (uint64_t)(c.blasNodeCount + c.tlasNodeCount) * sizeof(WideNode) + (uint64_t)c.nodeCount * sizeof(InstRecord);
+    out->msBlasBuild = c.msBlasBuild, out->msTlasBuild = c.msTlasBuild, out->msRefit = c.msRefit;
+    return GK_OK;
+}
+
+GkStatus gk_set_traversal_stats(GkContext* ctx, int enabled)
+{
+    GK_CHECK_CTX(ctx);
+    c.travStats = enabled != 0;
+    GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), c.stream));
+    return GK_OK;
+}
+
+void* gk_stream(GkContext* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+
+GkStatus gk_set_ray_capture(GkContext* ctx, int wave)
+{
+    GK_CHECK_CTX(ctx);
+    c.captureWave = wave;
+    return GK_OK;
+}
+
+GkStatus gk_get_captured_rays(GkContext* ctx, float* rays, uint32_t capacity, uint32_t* count)
+{
+    GK_CHECK_CTX(ctx);
+    if (!count) return GK_ERR_INVALID_ARGUMENT;
+    const uint32_t n = c.capturedCount < capacity ? c.capturedCount : capacity;
+    *count = c.capturedCount;
+    if (rays && n) {
+        GK_CUDA(cudaMemcpyAsync(rays, c.dCapture.p, 32 * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+        GK_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return GK_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,677 @@
+// gk_bvh_build.cu — GPU construction and refit of the acceleration structures.
+//
+// Replaces, on the device:
+//   vkCmdBuildAccelerationStructuresKHR for the BLAS set ..... RayTraceBaseRenderer.cpp:298-362
+//   the per-dirty-frame TLAS rebuild ......................... RayTraceBaseRenderer.cpp:176-228,
+//                                                             TopLevelAccelerationStructure.cpp:73-111
+//   tinybvh BVH::Build / BLASInstance::Update on the CPU side  tiny_bvh.h:1565-1766, 6718-6758
+//
+// Pipeline (all kernels on the context stream):
+//   1. group bounds      one atomic min/max box per model (BLAS forest) or for the scene (TLAS)
+//   2. Morton keys       64-bit key = group << 42 | 42-bit Morton code of the box centre
+//   3. radix sort        cub::DeviceRadixSort (library call; the one non-hand-written step)
+//   4. Karras 2012       binary radix tree over the sorted keys, every model at once: a model's
+//                        keys share the group prefix, so the tree contains one subtree per model
+//   5. bounds            bottom-up box propagation with arrival counters
+//   6. collapse          top-down, level-synchronous: each 8-wide node absorbs the binary nodes
+//                        with the largest surface area until it has 8 children
+//   7. quantise          child boxes -> 8 bits against the node box (also the refit path)
+// Refit (dynamic scenes) re-runs 5 and 7 only.
+//
+// Bytes per primitive (roofline model): keys+indices 12 B x (2 + 2x radix passes),
+// boxes 32 B r/w, binary node 40 B, wide node 128 B / ~3 prims.
+#include "gk_context.h"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace gk {
+
+DevBuf<float4>& sceneTriPositions();
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ void atomicMinFloat(float* addr, float v)
+{
+    // monotone int mapping of IEEE floats
+    if (v >= 0) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomicMaxFloat(float* addr, float v)
+{
+    if (v >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void k_init_group_bounds(float4* lo, float4* hi, uint32_t groups)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    lo[g] = make_float4(kFar, kFar, kFar, 0);
+    hi[g] = make_float4(-kFar, -kFar, -kFar, 0);
+}
+
+__global__ void k_group_bounds(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ group, uint32_t n,
+                               float4* glo, float4* ghi)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = plo[i], b = phi[i];
+    if (a.x > b.x) return; // empty box (hidden instance)
+    const uint32_t g = group ? group[i] : 0;
+    // warp-aggregate when the whole warp targets one group (the common case)
+    const unsigned full = __activemask();
+    const uint32_t g0 = __shfl_sync(full, g, __ffs(full) - 1);
+    if (__all_sync(full, g == g0)) {
+        float lx = a.x, ly = a.y, lz = a.z, hx = b.x, hy = b.y, hz = b.z;
+        for (int o = 16; o; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(full, lx, o)), ly = fminf(ly, __shfl_xor_sync(full, ly, o)), lz = fminf(lz, __shfl_xor_sync(full, lz, o));
+            hx = fmaxf(hx, __shfl_xor_sync(full, hx, o)), hy = fmaxf(hy, __shfl_xor_sync(full, hy, o)), hz = fmaxf(hz, __shfl_xor_sync(full, hz, o));
+        }
+        if (full == 0xffffffffu) {
+            if ((threadIdx.x & 31) == 0) {
+                atomicMinFloat(&glo[g].x, lx), atomicMinFloat(&glo[g].y, ly), atomicMinFloat(&glo[g].z, lz);
+                atomicMaxFloat(&ghi[g].x, hx), atomicMaxFloat(&ghi[g].y, hy), atomicMaxFloat(&ghi[g].z, hz);
+            }
+            return;
+        }
+    }
+    atomicMinFloat(&glo[g].x, a.x), atomicMinFloat(&glo[g].y, a.y), atomicMinFloat(&glo[g].z, a.z);
+    atomicMaxFloat(&ghi[g].x, b.x), atomicMaxFloat(&ghi[g].y, b.y), atomicMaxFloat(&ghi[g].z, b.z);
+}
+
+__device__ __forceinline__ unsigned long long spread14(uint32_t v)
+{
+    // 14 bits -> every third bit of a 42-bit word
+    unsigned long long x = v & 0x3fffu;
+    x = (x | (x << 32)) & 0x001f00000000ffffull;
+    x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+    x = (x | (x << 8)) & 0x100f00f00f00f00full;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ group, uint32_t n,
+                         const float4* __restrict__ glo, const float4* __restrict__ ghi, unsigned long long* __restrict__ keys, uint32_t* __restrict__ order)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = plo[i], b = phi[i];
+    const uint32_t g = group ? group[i] : 0;
+    const float4 gl = glo[g], gh = ghi[g];
+    float cx = 0.5f, cy = 0.5f, cz = 0.5f;
+    if (a.x <= b.x) {
+        const float ex = gh.x - gl.x, ey = gh.y - gl.y, ez = gh.z - gl.z;
+        cx = ex > 0 ? ((a.x + b.x) * 0.5f - gl.x) / ex : 0.5f;
+        cy = ey > 0 ? ((a.y + b.y) * 0.5f - gl.y) / ey : 0.5f;
+        cz = ez > 0 ? ((a.z + b.z) * 0.5f - gl.z) / ez : 0.5f;
+    }
+    const uint32_t qx = min(16383u, (uint32_t)(fmaxf(cx, 0.f) * 16384.f)), qy = min(16383u, (uint32_t)(fmaxf(cy, 0.f) * 16384.f)),
+                   qz = min(16383u, (uint32_t)(fmaxf(cz, 0.f) * 16384.f));
+    const unsigned long long m = (spread14(qx) << 2) | (spread14(qy) << 1) | spread14(qz);
+    keys[i] = ((unsigned long long)g << 42) | m;
+    order[i] = i;
+}
+
+// ------------------------------------------------------------------ Karras radix tree
+__device__ __forceinline__ int deltaKeys(const unsigned long long* __restrict__ keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((unsigned)i ^ (unsigned)j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_radix_tree(const unsigned long long* __restrict__ keys, int n, uint32_t* __restrict__ left, uint32_t* __restrict__ right,
+                             uint32_t* __restrict__ parentI, uint32_t* __restrict__ parentL, uint32_t* __restrict__ first, uint32_t* __restrict__ last)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (deltaKeys(keys, n, i, i + 1) - deltaKeys(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = deltaKeys(keys, n, i, i - d);
+    int lmax = 2;
+    while (deltaKeys(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (deltaKeys(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = deltaKeys(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (deltaKeys(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const uint32_t L = (lo == gamma) ? (kLeafBit | (uint32_t)gamma) : (uint32_t)gamma;
+    const uint32_t R = (hi == gamma + 1) ? (kLeafBit | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+    left[i] = L, right[i] = R;
+    first[i] = (uint32_t)lo, last[i] = (uint32_t)hi;
+    if (L & kLeafBit) parentL[gamma] = (uint32_t)i; else parentI[gamma] = (uint32_t)i;
+    if (R & kLeafBit) parentL[gamma + 1] = (uint32_t)i; else parentI[gamma + 1] = (uint32_t)i;
+    if (i == 0) parentI[0] = kInvalid;
+}
+
+__global__ void k_leaf_boxes(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ order, uint32_t n,
+                             float4* __restrict__ llo, float4* __restrict__ lhi)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t p = order[k];
+    llo[k] = plo[p], lhi[k] = phi[p];
+}
+
+__global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right, const uint32_t* __restrict__ parentI,
+                                   const uint32_t* __restrict__ parentL, const float4* llo, const float4* lhi, float4* ilo, float4* ihi, int* flags)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || n < 2) return;
+    uint32_t cur = parentL[k];
+    while (cur != kInvalid) {
+        __threadfence();
+        if (atomicAdd(&flags[cur], 1) == 0) return; // first arrival: the sibling subtree finishes the job
+        const uint32_t L = left[cur], R = right[cur];
+        const volatile float4* pl0 = (L & kLeafBit) ? llo + (L & 0x7fffffffu) : ilo + L;
+        const volatile float4* ph0 = (L & kLeafBit) ? lhi + (L & 0x7fffffffu) : ihi + L;
+        const volatile float4* pl1 = (R & kLeafBit) ? llo + (R & 0x7fffffffu) : ilo + R;
+        const volatile float4* ph1 = (R & kLeafBit) ? lhi + (R & 0x7fffffffu) : ihi + R;
+        const float lx = fminf(pl0->x, pl1->x), ly = fminf(pl0->y, pl1->y), lz = fminf(pl0->z, pl1->z);
+        const float hx = fmaxf(ph0->x, ph1->x), hy = fmaxf(ph0->y, ph1->y), hz = fmaxf(ph0->z, ph1->z);
+        ilo[cur] = make_float4(lx, ly, lz, 0), ihi[cur] = make_float4(hx, hy, hz, 0);
+        cur = parentI[cur];
+    }
+}
+
+// ------------------------------------------------------------------ per-group roots
+__global__ void k_group_roots(const unsigned long long* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
+                              uint32_t* __restrict__ groupRoot)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { // single-primitive groups: the leaf is the root
+        const unsigned long long g = keys[i] >> 42;
+        const bool lonelyL = (i == 0) || (keys[i - 1] >> 42) != g, lonelyR = (i == n - 1) || (keys[i + 1] >> 42) != g;
+        if (lonelyL && lonelyR) groupRoot[g] = kLeafBit | i;
+    }
+    if (i + 1 < n) {
+        const uint32_t a = first[i], b = last[i];
+        const unsigned long long g = keys[a] >> 42;
+        if ((keys[b] >> 42) == g && (a == 0 || (keys[a - 1] >> 42) != g) && (b == n - 1 || (keys[b + 1] >> 42) != g)) groupRoot[g] = i;
+    }
+}
+
+// ------------------------------------------------------------------ triangle records in leaf order
+__global__ void k_write_tri_records(const float4* __restrict__ triP, const uint32_t* __restrict__ order, const ModelInfo* __restrict__ models,
+                                    const uint32_t* __restrict__ group, uint32_t n, TriRecord* __restrict__ out)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t p = order[k];
+    const float4 a = triP[(size_t)p * 3], b = triP[(size_t)p * 3 + 1], c = triP[(size_t)p * 3 + 2];
+    TriRecord r;
+    r.v0x = a.x, r.v0y = a.y, r.v0z = a.z;
+    r.prim = p - models[group[p]].triOffset; // triangle index inside its model
+    r.e1x = __fsub_rn(b.x, a.x), r.e1y = __fsub_rn(b.y, a.y), r.e1z = __fsub_rn(b.z, a.z);
+    r.e2x = __fsub_rn(c.x, a.x), r.e2y = __fsub_rn(c.y, a.y), r.e2z = __fsub_rn(c.z, a.z);
+    r.pad0 = r.pad1 = 0;
+    float4* o = reinterpret_cast<float4*>(out + k);
+    const float4* s = reinterpret_cast<const float4*>(&r);
+    o[0] = s[0], o[1] = s[1], o[2] = s[2];
+}
+
+// ------------------------------------------------------------------ collapse to 8-wide
+struct Bvh2View {
+    const uint32_t *left, *right, *first, *last, *order;
+    const float4 *ilo, *ihi, *llo, *lhi;
+};
+
+__device__ __forceinline__ float boxArea(float4 lo, float4 hi)
+{
+    const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return ex * ey + ey * ez + ez * ex;
+}
+
+// Turns a binary-tree reference into the reference stored in a wide node.
+__device__ __forceinline__ uint32_t finalLeafRef(const Bvh2View& B, uint32_t ref, uint32_t leafMax, bool tlas, bool& isLeaf)
+{
+    if (ref & kLeafBit) {
+        isLeaf = true;
+        const uint32_t k = ref & 0x7fffffffu;
+        return tlas ? (kLeafBit | B.order[k]) : (kLeafBit | (k << 3));
+    }
+    const uint32_t size = B.last[ref] - B.first[ref] + 1;
+    if (!tlas && size <= leafMax) {
+        isLeaf = true;
+        return kLeafBit | (B.first[ref] << 3) | (size - 1);
+    }
+    isLeaf = false;
+    return ref;
+}
+
+// Seeds one collapse task per group whose root needs a wide node; others get their leaf reference.
+__global__ void k_collapse_seed(Bvh2View B, const uint32_t* __restrict__ groupRoot, uint32_t groups, uint32_t leafMax, int tlas, uint32_t* __restrict__ rootRef,
+                                uint32_t* __restrict__ tasks, uint32_t* __restrict__ counters /* [0]=taskCount [1]=wideCount */)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const uint32_t r = groupRoot[g];
+    if (r == kInvalid) {
+        rootRef[g] = kInvalid;
+        return;
+    }
+    bool leaf;
+    const uint32_t ref = finalLeafRef(B, r, leafMax, tlas != 0, leaf);
+    if (leaf) {
+        rootRef[g] = ref;
+        return;
+    }
+    const uint32_t w = atomicAdd(&counters[1], 1u);
+    const uint32_t t = atomicAdd(&counters[0], 1u);
+    tasks[2 * t] = r, tasks[2 * t + 1] = w;
+    rootRef[g] = w;
+}
+
+__global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksIn, uint32_t taskCount, uint32_t* __restrict__ tasksOut,
+                                 uint32_t* __restrict__ counters /* [0]=outCount [1]=wideCount */, WideNode* __restrict__ nodes, uint32_t leafMax, int tlas,
+                                 uint32_t nodeCapacity)
+{
+    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= taskCount) return;
+    const uint32_t b2 = tasksIn[2 * ti], w = tasksIn[2 * ti + 1];
+    uint32_t slot[8];
+    int cnt = 2;
+    slot[0] = B.left[b2], slot[1] = B.right[b2];
+    // greedy: open the internal child with the largest box until 8 slots are used
+    for (;;) {
+        if (cnt == 8) break;
+        int best = -1;
+        float bestA = -1.f;
+        for (int i = 0; i < cnt; ++i) {
+            const uint32_t r = slot[i];
+            if (r & kLeafBit) continue;
+            if (!tlas && (B.last[r] - B.first[r] + 1) <= leafMax) continue;
+            const float a = boxArea(B.ilo[r], B.ihi[r]);
+            if (a > bestA) bestA = a, best = i;
+        }
+        if (best < 0) break;
+        const uint32_t r = slot[best];
+        // keep the key order of the children: left stays, right is inserted after it
+        for (int i = cnt; i > best + 1; --i) slot[i] = slot[i - 1];
+        slot[best] = B.left[r], slot[best + 1] = B.right[r];
+        ++cnt;
+    }
+    uint32_t refs[8];
+    bool leaf[8];
+    int internal = 0;
+    for (int i = 0; i < cnt; ++i) {
+        refs[i] = finalLeafRef(B, slot[i], leafMax, tlas != 0, leaf[i]);
+        if (!leaf[i]) ++internal;
+    }
+    uint32_t base = 0, tbase = 0;
+    if (internal) {
+        base = atomicAdd(&counters[1], (uint32_t)internal);
+        tbase = atomicAdd(&counters[0], (uint32_t)internal);
+    }
+    if (w >= nodeCapacity || base + internal > nodeCapacity) return; // capacity is an upper bound; never expected
+    WideNode n;
+    n.ox = n.oy = n.oz = 0.f;
+    n.ex = n.ey = n.ez = 127;
+    n.count = (uint8_t)cnt;
+    int k = 0;
+    for (int i = 0; i < 8; ++i) {
+        if (i < cnt) {
+            n.src[i] = slot[i];
+            if (leaf[i]) n.child[i] = refs[i];
+            else {
+                n.child[i] = base + k;
+                tasksOut[2 * (tbase + k)] = refs[i], tasksOut[2 * (tbase + k) + 1] = base + k;
+                ++k;
+            }
+        } else {
+            n.src[i] = kInvalid, n.child[i] = kInvalid;
+        }
+        for (int a = 0; a < 3; ++a) n.qlo[a][i] = 255, n.qhi[a][i] = 0;
+    }
+    uint4* o = reinterpret_cast<uint4*>(nodes + w);
+    const uint4* s = reinterpret_cast<const uint4*>(&n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = s[i];
+}
+
+// Per-axis step exponent: the smallest power of two with extent / step <= 250, but never
+// finer than 2^-18 of the coordinate magnitude (so that origin - step is a distinct float).
+__device__ __forceinline__ int chooseExponent(float lo, float hi)
+{
+    const float extent = hi - lo;
+    int e = -126;
+    if (extent > 0.f) {
+        const float x = extent / 250.f;
+        int ex = ilogbf(x);
+        if (ldexpf(1.f, ex) < x) ++ex;
+        e = ex;
+    }
+    const float mag = fmaxf(fabsf(lo), fabsf(hi));
+    if (mag > 0.f) e = max(e, ilogbf(mag) - 18);
+    return min(max(e, -120), 120);
+}
+
+__global__ void k_quantise(Bvh2View B, WideNode* __restrict__ nodes, uint32_t count)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= count) return;
+    WideNode n;
+    {
+        uint4* d = reinterpret_cast<uint4*>(&n);
+        const uint4* s = reinterpret_cast<const uint4*>(nodes + w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = s[i];
+    }
+    float4 lo[8], hi[8];
+    float4 nlo = make_float4(kFar, kFar, kFar, 0), nhi = make_float4(-kFar, -kFar, -kFar, 0);
+    for (int i = 0; i < (int)n.count; ++i) {
+        const uint32_t r = n.src[i];
+        if (r & kLeafBit) lo[i] = B.llo[r & 0x7fffffffu], hi[i] = B.lhi[r & 0x7fffffffu];
+        else lo[i] = B.ilo[r], hi[i] = B.ihi[r];
+        if (lo[i].x <= hi[i].x) {
+            nlo.x = fminf(nlo.x, lo[i].x), nlo.y = fminf(nlo.y, lo[i].y), nlo.z = fminf(nlo.z, lo[i].z);
+            nhi.x = fmaxf(nhi.x, hi[i].x), nhi.y = fmaxf(nhi.y, hi[i].y), nhi.z = fmaxf(nhi.z, hi[i].z);
+        }
+    }
+    if (nlo.x > nhi.x) nlo = nhi = make_float4(0, 0, 0, 0); // every child empty
+    const int e[3] = {chooseExponent(nlo.x, nhi.x), chooseExponent(nlo.y, nhi.y), chooseExponent(nlo.z, nhi.z)};
+    const float step[3] = {ldexpf(1.f, e[0]), ldexpf(1.f, e[1]), ldexpf(1.f, e[2])};
+    const float org[3] = {nlo.x - step[0], nlo.y - step[1], nlo.z - step[2]};
+    n.ox = org[0], n.oy = org[1], n.oz = org[2];
+    n.ex = (uint8_t)(e[0] + 127), n.ey = (uint8_t)(e[1] + 127), n.ez = (uint8_t)(e[2] + 127);
+    for (int i = 0; i < 8; ++i) {
+        if (i < (int)n.count && lo[i].x <= hi[i].x) {
+            const float l3[3] = {lo[i].x, lo[i].y, lo[i].z}, h3[3] = {hi[i].x, hi[i].y, hi[i].z};
+            for (int a = 0; a < 3; ++a) {
+                const float ql = floorf((l3[a] - org[a]) / step[a] - 0.015625f), qh = ceilf((h3[a] - org[a]) / step[a] + 0.015625f);
+                n.qlo[a][i] = (uint8_t)fminf(fmaxf(ql, 0.f), 255.f);
+                n.qhi[a][i] = (uint8_t)fminf(fmaxf(qh, 0.f), 255.f);
+            }
+        } else {
+            for (int a = 0; a < 3; ++a) n.qlo[a][i] = 255, n.qhi[a][i] = 0;
+        }
+    }
+    uint4* o = reinterpret_cast<uint4*>(nodes + w);
+    const uint4* s = reinterpret_cast<const uint4*>(&n);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) o[i] = s[i]; // src[] unchanged
+}
+
+// ------------------------------------------------------------------ instances
+// BLASInstance::Update + InvertTransform (tiny_bvh.h:6718-6758): cofactor inverse with the
+// reference's term order, world box from the 8 corners of the BLAS root box.
+__device__ void invert4x4RowMajor(const float* T, float* o)
+{
+#define M3(a, b, c) __fmul_rn(__fmul_rn(T[a], T[b]), T[c])
+#define S6(p0, p1, p2, p3, p4, p5) __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3), p4), p5)
+    o[0] = S6(M3(5, 10, 15), -M3(5, 11, 14), -M3(9, 6, 15), M3(9, 7, 14), M3(13, 6, 11), -M3(13, 7, 10));
+    o[1] = S6(-M3(1, 10, 15), M3(1, 11, 14), M3(9, 2, 15), -M3(9, 3, 14), -M3(13, 2, 11), M3(13, 3, 10));
+    o[2] = S6(M3(1, 6, 15), -M3(1, 7, 14), -M3(5, 2, 15), M3(5, 3, 14), M3(13, 2, 7), -M3(13, 3, 6));
+    o[3] = S6(-M3(1, 6, 11), M3(1, 7, 10), M3(5, 2, 11), -M3(5, 3, 10), -M3(9, 2, 7), M3(9, 3, 6));
+    o[4] = S6(-M3(4, 10, 15), M3(4, 11, 14), M3(8, 6, 15), -M3(8, 7, 14), -M3(12, 6, 11), M3(12, 7, 10));
+    o[5] = S6(M3(0, 10, 15), -M3(0, 11, 14), -M3(8, 2, 15), M3(8, 3, 14), M3(12, 2, 11), -M3(12, 3, 10));
+    o[6] = S6(-M3(0, 6, 15), M3(0, 7, 14), M3(4, 2, 15), -M3(4, 3, 14), -M3(12, 2, 7), M3(12, 3, 6));
+    o[7] = S6(M3(0, 6, 11), -M3(0, 7, 10), -M3(4, 2, 11), M3(4, 3, 10), M3(8, 2, 7), -M3(8, 3, 6));
+    o[8] = S6(M3(4, 9, 15), -M3(4, 11, 13), -M3(8, 5, 15), M3(8, 7, 13), M3(12, 5, 11), -M3(12, 7, 9));
+    o[9] = S6(-M3(0, 9, 15), M3(0, 11, 13), M3(8, 1, 15), -M3(8, 3, 13), -M3(12, 1, 11), M3(12, 3, 9));
+    o[10] = S6(M3(0, 5, 15), -M3(0, 7, 13), -M3(4, 1, 15), M3(4, 3, 13), M3(12, 1, 7), -M3(12, 3, 5));
+    o[11] = S6(-M3(0, 5, 11), M3(0, 7, 9), M3(4, 1, 11), -M3(4, 3, 9), -M3(8, 1, 7), M3(8, 3, 5));
+    o[12] = S6(-M3(4, 9, 14), M3(4, 10, 13), M3(8, 5, 14), -M3(8, 6, 13), -M3(12, 5, 10), M3(12, 6, 9));
+    o[13] = S6(M3(0, 9, 14), -M3(0, 10, 13), -M3(8, 1, 14), M3(8, 2, 13), M3(12, 1, 10), -M3(12, 2, 9));
+    o[14] = S6(-M3(0, 5, 14), M3(0, 6, 13), M3(4, 1, 14), -M3(4, 2, 13), -M3(12, 1, 6), M3(12, 2, 5));
+    o[15] = S6(M3(0, 5, 10), -M3(0, 6, 9), -M3(4, 1, 10), M3(4, 2, 9), M3(8, 1, 6), -M3(8, 2, 5));
+#undef M3
+#undef S6
+    const float det = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], o[0]), __fmul_rn(T[1], o[4])), __fmul_rn(T[2], o[8])), __fmul_rn(T[3], o[12]));
+    if (det == 0) {
+        for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? 1.f : 0.f; // tinybvh leaves the identity in place
+        return;
+    }
+    const float invdet = __fdiv_rn(1.0f, det);
+    for (int i = 0; i < 16; ++i) o[i] = __fmul_rn(o[i], invdet);
+}
+
+__global__ void k_update_instances(const GkNodeProxy* __restrict__ nodes, uint32_t count, const ModelInfo* __restrict__ models, uint32_t modelCount,
+                                   InstRecord* __restrict__ inst, float4* __restrict__ plo, float4* __restrict__ phi)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const GkNodeProxy& P = nodes[i];
+    InstRecord R;
+    const uint32_t model = P.modelId / 10;
+    const bool visible = P.visible && !P.nort && model < modelCount; // RayTraceBaseRenderer.cpp:188-189
+    float T[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) T[r * 4 + c] = P.worldTS[c * 4 + r]; // glm column-major -> tinybvh row-major
+    invert4x4RowMajor(T, R.invT);
+    R.node = i, R.model = model, R.pad = 0;
+    R.blasRoot = visible ? models[model].blasRoot : kInvalid;
+    float4 lo = make_float4(kFar, kFar, kFar, 0), hi = make_float4(-kFar, -kFar, -kFar, 0);
+    if (visible && R.blasRoot != kInvalid) {
+        const ModelInfo& M = models[model];
+        for (int j = 0; j < 8; ++j) {
+            const f3 p = mk3(j & 1 ? M.bmax[0] : M.bmin[0], j & 2 ? M.bmax[1] : M.bmin[1], j & 4 ? M.bmax[2] : M.bmin[2]);
+            const f3 t = xformPoint(p, T);
+            lo.x = fminf(lo.x, t.x), lo.y = fminf(lo.y, t.y), lo.z = fminf(lo.z, t.z);
+            hi.x = fmaxf(hi.x, t.x), hi.y = fmaxf(hi.y, t.y), hi.z = fmaxf(hi.z, t.z);
+        }
+    }
+    plo[i] = lo, phi[i] = hi;
+    float4* o = reinterpret_cast<float4*>(inst + i);
+    const float4* s = reinterpret_cast<const float4*>(&R);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) o[k] = s[k];
+}
+
+__global__ void k_model_bounds_from_groups(ModelInfo* models, uint32_t modelCount, const float4* glo, const float4* ghi, const uint32_t* rootRef)
+{
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= modelCount) return;
+    models[m].bmin[0] = glo[m].x, models[m].bmin[1] = glo[m].y, models[m].bmin[2] = glo[m].z, models[m].bmin[3] = 0;
+    models[m].bmax[0] = ghi[m].x, models[m].bmax[1] = ghi[m].y, models[m].bmax[2] = ghi[m].z, models[m].bmax[3] = 0;
+    models[m].blasRoot = rootRef[m];
+}
+
+// ------------------------------------------------------------------ host orchestration
+void Lbvh::release()
+{
+    keys.release(), keysAlt.release(), order.release(), orderAlt.release(), left.release(), right.release(), parentI.release(), parentL.release();
+    first.release(), last.release(), ilo.release(), ihi.release(), llo.release(), lhi.release(), plo.release(), phi.release(), group.release(), flags.release();
+}
+
+static inline unsigned gridFor(size_t n, unsigned block = 256) { return (unsigned)((n + block - 1) / block); }
+
+// Steps 1-5 over T.plo/T.phi/T.group (group may be null => one group).
+static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint32_t groups, int keyBits)
+{
+    const uint32_t n = T.n;
+    cudaStream_t st = c.stream;
+    GK_CUDA(T.keys.reserve(n));
+    GK_CUDA(T.keysAlt.reserve(n));
+    GK_CUDA(T.order.reserve(n));
+    GK_CUDA(T.orderAlt.reserve(n));
+    GK_CUDA(T.left.reserve(n));
+    GK_CUDA(T.right.reserve(n));
+    GK_CUDA(T.parentI.reserve(n));
+    GK_CUDA(T.parentL.reserve(n));
+    GK_CUDA(T.first.reserve(n));
+    GK_CUDA(T.last.reserve(n));
+    GK_CUDA(T.ilo.reserve(n));
+    GK_CUDA(T.ihi.reserve(n));
+    GK_CUDA(T.llo.reserve(n));
+    GK_CUDA(T.lhi.reserve(n));
+    GK_CUDA(T.flags.reserve(n));
+    GK_CUDA(c.dGroupLo.reserve(groups));
+    GK_CUDA(c.dGroupHi.reserve(groups));
+    k_init_group_bounds<<<gridFor(groups), 256, 0, st>>>(c.dGroupLo.p, c.dGroupHi.p, groups);
+    k_group_bounds<<<gridFor(n), 256, 0, st>>>(T.plo.p, T.phi.p, group, n, c.dGroupLo.p, c.dGroupHi.p);
+    k_morton<<<gridFor(n), 256, 0, st>>>(T.plo.p, T.phi.p, group, n, c.dGroupLo.p, c.dGroupHi.p, T.keysAlt.p, T.orderAlt.p);
+    size_t tempBytes = 0;
+    GK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, T.keysAlt.p, T.keys.p, T.orderAlt.p, T.order.p, (int)n, 0, keyBits, st));
+    GK_CUDA(c.dSortTemp.reserve(tempBytes));
+    tempBytes = c.dSortTemp.bytes();
+    GK_CUDA(cub::DeviceRadixSort::SortPairs(c.dSortTemp.p, tempBytes, T.keysAlt.p, T.keys.p, T.orderAlt.p, T.order.p, (int)n, 0, keyBits, st));
+    if (n > 1) k_radix_tree<<<gridFor(n - 1), 256, 0, st>>>(T.keys.p, (int)n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, T.first.p, T.last.p);
+    GK_CUDA(cudaGetLastError());
+    return GK_OK;
+}
+
+static GkStatus propagateBounds(Context& c, Lbvh& T)
+{
+    const uint32_t n = T.n;
+    cudaStream_t st = c.stream;
+    k_leaf_boxes<<<gridFor(n), 256, 0, st>>>(T.plo.p, T.phi.p, T.order.p, n, T.llo.p, T.lhi.p);
+    if (n > 1) {
+        GK_CUDA(cudaMemsetAsync(T.flags.p, 0, sizeof(int) * n, st));
+        k_propagate_bounds<<<gridFor(n), 256, 0, st>>>(n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, T.llo.p, T.lhi.p, T.ilo.p, T.ihi.p, T.flags.p);
+    }
+    GK_CUDA(cudaGetLastError());
+    return GK_OK;
+}
+
+static Bvh2View viewOf(const Lbvh& T)
+{
+    Bvh2View B;
+    B.left = T.left.p, B.right = T.right.p, B.first = T.first.p, B.last = T.last.p, B.order = T.order.p;
+    B.ilo = T.ilo.p, B.ihi = T.ihi.p, B.llo = T.llo.p, B.lhi = T.lhi.p;
+    return B;
+}
+
+// Step 6+7.  rootRef (device, one per group) receives the wide root reference of each group.
+static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax, bool tlas, DevBuf<WideNode>& nodes, uint32_t& nodeCount, uint32_t* dRootRef)
+{
+    const uint32_t n = T.n;
+    cudaStream_t st = c.stream;
+    const uint32_t capacity = n + groups + 8; // a wide node has >= 2 children: at most n-1 nodes
+    GK_CUDA(nodes.reserve(capacity));
+    GK_CUDA(c.dTaskA.reserve(2 * (size_t)capacity));
+    GK_CUDA(c.dTaskB.reserve(2 * (size_t)capacity));
+    GK_CUDA(c.dCounters.reserve(8));
+    GK_CUDA(c.dGroupRoot.reserve(groups));
+    GK_CUDA(cudaMemsetAsync(c.dGroupRoot.p, 0xff, sizeof(uint32_t) * groups, st));
+    GK_CUDA(cudaMemsetAsync(c.dCounters.p, 0, sizeof(uint32_t) * 8, st));
+    const Bvh2View B = viewOf(T);
+    k_group_roots<<<gridFor(n), 256, 0, st>>>(T.keys.p, n, T.first.p, T.last.p, c.dGroupRoot.p);
+    k_collapse_seed<<<gridFor(groups), 256, 0, st>>>(B, c.dGroupRoot.p, groups, leafMax, tlas ? 1 : 0, dRootRef, c.dTaskA.p, c.dCounters.p);
+    uint32_t* in = c.dTaskA.p;
+    uint32_t* out = c.dTaskB.p;
+    uint32_t h[2] = {0, 0};
+    for (int level = 0; level < 128; ++level) {
+        GK_CUDA(cudaMemcpyAsync(h, c.dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        const uint32_t tasks = h[0];
+        if (tasks == 0) break;
+        GK_CUDA(cudaMemsetAsync(c.dCounters.p, 0, sizeof(uint32_t), st));
+        k_collapse_level<<<gridFor(tasks, 128), 128, 0, st>>>(B, in, tasks, out, c.dCounters.p, nodes.p, leafMax, tlas ? 1 : 0, capacity);
+        std::swap(in, out);
+    }
+    GK_CUDA(cudaMemcpyAsync(h, c.dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    nodeCount = h[1];
+    if (nodeCount > capacity) {
+        setLastError("wide-node pool overflow");
+        return GK_ERR_OUT_OF_MEMORY;
+    }
+    if (nodeCount) k_quantise<<<gridFor(nodeCount, 128), 128, 0, st>>>(B, nodes.p, nodeCount);
+    GK_CUDA(cudaGetLastError());
+    return GK_OK;
+}
+
+GkStatus buildBlasForest(Context& c)
+{
+    cudaStream_t st = c.stream;
+    Lbvh& T = c.blasTree;
+    const uint32_t groups = (uint32_t)c.models.size();
+    if (groups >= (1u << 22)) {
+        setLastError("too many models");
+        return GK_ERR_UNSUPPORTED;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    GkStatus s = buildRadixTree(c, T, T.group.p, groups, 64);
+    if (s != GK_OK) return s;
+    GK_CUDA(c.dTris.reserve(T.n));
+    k_write_tri_records<<<gridFor(T.n), 256, 0, st>>>(sceneTriPositions().p, T.order.p, c.dModels.p, T.group.p, T.n, c.dTris.p);
+    s = propagateBounds(c, T);
+    if (s != GK_OK) return s;
+    DevBuf<uint32_t> rootRef;
+    GK_CUDA(rootRef.reserve(groups));
+    s = collapse(c, T, groups, 4, false, c.dBlasNodes, c.blasNodeCount, rootRef.p);
+    if (s != GK_OK) return s;
+    k_model_bounds_from_groups<<<gridFor(groups), 256, 0, st>>>(c.dModels.p, groups, c.dGroupLo.p, c.dGroupHi.p, rootRef.p);
+    cudaEventRecord(e1, st);
+    GK_CUDA(cudaMemcpyAsync(c.models.data(), c.dModels.p, sizeof(ModelInfo) * groups, cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c.msBlasBuild, e0, e1);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    rootRef.release();
+    return GK_OK;
+}
+
+GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, bool refit)
+{
+    cudaStream_t st = c.stream;
+    if (!c.haveScene) {
+        setLastError("gk_update_instances: no scene uploaded");
+        return GK_ERR_NOT_READY;
+    }
+    if (count == 0 || !nodes) {
+        setLastError("gk_update_instances: empty instance list");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    Lbvh& T = c.tlasTree;
+    if (refit && (!c.haveInstances || count != T.n)) refit = false;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    GK_CUDA(c.dNodes.reserve(count));
+    GK_CUDA(cudaMemcpyAsync(c.dNodes.p, nodes, sizeof(GkNodeProxy) * count, cudaMemcpyHostToDevice, st));
+    c.nodeCount = count;
+    T.n = count;
+    GK_CUDA(T.plo.reserve(count));
+    GK_CUDA(T.phi.reserve(count));
+    GK_CUDA(c.dInst.reserve(count));
+    k_update_instances<<<gridFor(count, 128), 128, 0, st>>>(c.dNodes.p, count, c.dModels.p, (uint32_t)c.models.size(), c.dInst.p, T.plo.p, T.phi.p);
+    GkStatus s;
+    if (!refit) {
+        s = buildRadixTree(c, T, nullptr, 1, 42);
+        if (s != GK_OK) return s;
+    }
+    s = propagateBounds(c, T);
+    if (s != GK_OK) return s;
+    if (!refit) {
+        DevBuf<uint32_t> rootRef;
+        GK_CUDA(rootRef.reserve(1));
+        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.tlasNodeCount, rootRef.p);
+        if (s != GK_OK) return s;
+        GK_CUDA(cudaMemcpyAsync(&c.tlasRoot, rootRef.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        rootRef.release();
+    } else if (c.tlasNodeCount) {
+        k_quantise<<<gridFor(c.tlasNodeCount, 128), 128, 0, st>>>(viewOf(T), c.dTlasNodes.p, c.tlasNodeCount);
+    }
+    cudaEventRecord(e1, st);
+    GK_CUDA(cudaGetLastError());
+    // instanced triangle count (host side, from the proxies the caller handed over)
+    uint64_t inst = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t m = nodes[i].modelId / 10;
+        if (nodes[i].visible && !nodes[i].nort && m < c.models.size()) inst += c.models[m].triCount;
+    }
+    c.instancedTris = inst;
+    GK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (refit) c.msRefit = ms; else c.msTlasBuild = ms;
+    c.stats.msBvh = ms;
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    c.haveInstances = true;
+    return GK_OK;
+}
+
+} // namespace gk

@@ -1,0 +1,186 @@
+// gk_context.h — host-side state behind a GkContext handle.
+#pragma once
+#include "../../include/gknext_cuda.h"
+#include "gk_bvh.cuh"
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+namespace gk {
+
+void setLastError(const std::string& s);
+
+#define GK_CUDA(expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess) {                                                                              \
+            gk::setLastError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+            return GK_ERR_CUDA;                                                                               \
+        }                                                                                                     \
+    } while (0)
+
+// growable device buffer
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0; // elements
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr, cap = 0;
+        size_t want = n + n / 8 + 16;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr, cap = 0;
+    }
+    size_t bytes() const { return cap * sizeof(T); }
+};
+
+// Binary radix tree (Karras 2012) over `n` primitives, kept for refit.
+struct Lbvh {
+    uint32_t n = 0;
+    DevBuf<unsigned long long> keys, keysAlt;
+    DevBuf<uint32_t> order, orderAlt; // sorted position -> primitive
+    DevBuf<uint32_t> left, right;     // per internal node (n-1)
+    DevBuf<uint32_t> parentI, parentL; // parent of internal node / of leaf (sorted position)
+    DevBuf<uint32_t> first, last;      // key range of each internal node
+    DevBuf<float4> ilo, ihi;           // internal-node boxes
+    DevBuf<float4> llo, lhi;           // leaf boxes in sorted order
+    DevBuf<float4> plo, phi;           // primitive boxes in primitive order
+    DevBuf<uint32_t> group;            // primitive -> group (model) id
+    DevBuf<int> flags;
+    void release();
+};
+
+struct ModelInfo { // per Assets::Model
+    uint32_t vertexOffset, vertexCount;
+    uint32_t indexOffset, indexCount; // into the concatenated index buffer
+    uint32_t triOffset, triCount;     // into the concatenated (unsorted) triangle list
+    uint32_t blasRoot;                // reference into blasNodes (leaf reference possible)
+    uint32_t pad;
+    float bmin[4], bmax[4];           // BLAS root box (BVH::aabbMin/aabbMax)
+};
+
+struct Planes {
+    void* p[GK_PLANE_COUNT] = {};
+    size_t bytes[GK_PLANE_COUNT] = {};
+};
+
+// SoA wavefront state, one slot per owned pixel ("path")
+struct PathState {
+    uint4* rng;
+    float4* posMat;      // current vertex position, w = material index (bits)
+    float4* nrmFlags;    // current vertex normal, w = packed bounce/sample/state flags (bits)
+    float4* dirT;        // current direction
+    float4* throughput;  // rayColor rgb, w unused
+    float4* primPosMat;  // primary vertex position, w = material index
+    float4* primNrm;     // primary vertex normal, w = |pixelOffset|
+    float4* accDiffuse;  // FinalColor accumulator, w = direct-light shadow term
+    float4* accSpec;     // FinalReflection accumulator
+    uint32_t* pixel;     // image pixel index of the path
+    uint32_t* rays;      // rays traced so far
+    float4* dofVertex;   // scratch for the depth-of-field re-trace (initial vertex position, w = raw material slot)
+    float4* dofNormal;   // initial vertex normal, w = node index bits
+};
+
+struct RayQueue {
+    float4* o_tmin; // origin.xyz, tmin
+    float4* d_tmax; // direction.xyz, tmax
+    uint32_t* path; // owning path
+    float4* hit_tuvp; // results: t, u, v, prim(bits)
+    uint32_t* hit_inst;
+    uint32_t* count; // device counter
+};
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t width = 0, height = 0;
+    uint32_t tileIndex = 0, tileCount = 1, tileRows = 16;
+    uint32_t ownedRows = 0, pathCount = 0;
+    uint32_t flags = 0;
+
+    // scene
+    bool haveScene = false, haveInstances = false, haveUbo = false;
+    std::vector<ModelInfo> models;
+    DevBuf<ModelInfo> dModels;
+    DevBuf<GkGPUVertex> dGpuVerts;
+    DevBuf<uint32_t> dIndices;
+    DevBuf<GkMaterial> dMaterials;
+    uint32_t materialCount = 0;
+    DevBuf<GkLightObject> dLights;
+    DevBuf<float4> dFaceNormals; // per triangle (model order): FCPUBLASVertInfo::normal
+    DevBuf<GkNodeProxy> dNodes;
+    uint32_t nodeCount = 0;
+    DevBuf<GkAmbientCube> dCubes;
+    DevBuf<GkVoxelData> dVoxels;
+    bool haveProbes = false;
+    uint64_t totalTris = 0, instancedTris = 0;
+
+    // acceleration structures
+    Lbvh blasTree, tlasTree;
+    DevBuf<TriRecord> dTris;
+    DevBuf<WideNode> dBlasNodes, dTlasNodes;
+    uint32_t blasNodeCount = 0, tlasNodeCount = 0;
+    DevBuf<InstRecord> dInst;
+    uint32_t tlasRoot = 0;
+    DevBuf<uint32_t> dTaskA, dTaskB, dCounters;
+    DevBuf<unsigned char> dSortTemp;
+    DevBuf<float4> dGroupLo, dGroupHi;
+    DevBuf<uint32_t> dGroupRoot;
+    float msBlasBuild = 0, msTlasBuild = 0, msRefit = 0;
+
+    // frame
+    GkUniformBufferObject ubo{};
+    GkUniformBufferObject* dUbo = nullptr;
+    Planes planes;
+    PathState paths{};
+    std::vector<void*> pathAllocs;
+    RayQueue extendQ[2]{}, shadowQ[2]{};
+    std::vector<void*> queueAllocs;
+    uint32_t* hCounts = nullptr; // pinned
+    TraversalStats* dTravStats = nullptr;
+    bool travStats = false;
+    GkFrameStats stats{};
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    std::vector<cudaEvent_t> evPool;
+    int captureWave = -1;
+    DevBuf<float4> dCapture;
+    uint32_t capturedCount = 0;
+    uint64_t frameIndex = 0;
+    bool pendingHistorySwap = false, tracedSinceFilter = false;
+
+    SceneView view() const
+    {
+        SceneView v;
+        v.tlasNodes = dTlasNodes.p, v.blasNodes = dBlasNodes.p, v.tris = dTris.p, v.inst = dInst.p;
+        v.tlasRoot = tlasRoot, v.instanceCount = nodeCount;
+        return v;
+    }
+};
+
+// gk_scene.cu
+GkStatus uploadScene(Context& c, const GkSceneDesc& d);
+// gk_bvh_build.cu
+GkStatus buildBlasForest(Context& c);
+GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, bool refit);
+// gk_integrator.cu
+GkStatus allocFrameResources(Context& c);
+void freeFrameResources(Context& c);
+GkStatus traceFrame(Context& c);
+GkStatus intersectDevice(Context& c, const float4* rays, uint32_t n, float* tuv, uint32_t* ids, bool anyHit);
+GkStatus raycastBatch(Context& c, const float* originDir, uint32_t n, GkRayCastResult* out);
+// gk_filters.cu
+GkStatus filterFrame(Context& c);
+void applyPendingHistorySwap(Context& c);
+
+} // namespace gk
+
+struct GkContext {
+    gk::Context c;
+};

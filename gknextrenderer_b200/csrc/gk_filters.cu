@@ -1,0 +1,376 @@
+// gk_filters.cu — temporal reprojection, joint-bilateral denoise + compose, history hand-over.
+//
+// Replaces
+//   Process.ReProject.comp.slang :60-181, dispatched three times per frame for diffuse, specular
+//     and albedo with push constants {needClamp, needSpatio} = {0,1},{0,1},{1,0}
+//     (src/Rendering/PathTracing/PathTracingRenderer.cpp:117-144)           -> k_reproject (ONE launch)
+//   Process.DenoiseJBF.comp.slang :96-195 (PathTracingRenderer.cpp:146-169)  -> k_denoise_jbf
+//   the three vkCmdCopyImage "copy pass" calls (:171-195) and the ObjectId0 -> ObjectId1 copy
+//     (src/Rendering/VulkanBaseRenderer.cpp:1287-1303)                       -> pointer swaps, 0 bytes
+//
+// Both kernels are HBM-bound streaming kernels.  A block owns a 32x8 pixel tile and stages the
+// halo it needs in shared memory with coalesced 8-byte (RGBA16F) row reads:
+//   reproject: source colour of the three channel sets, object ids and normals with a 2-pixel halo
+//              (the 5x5 spatial fallback and the 5x5 YCoCg clamp read the same 25 texels);
+//              history is gathered through L2 at the motion-vector target (4 taps).
+//   denoise  : diffuse with a 5-pixel halo (taps at -5,-3,..,5); spec/albedo/ids are centre-only.
+// Algorithmic bytes per pixel: reproject 96 B, denoise 48 B.
+// Images outside [0,W)x[0,H) read as 0 and are never written (Vulkan robust image access).
+// lerp(a,b,t) = a*(1-t) + b*t.
+#include "gk_context.h"
+#include <cuda_fp16.h>
+
+namespace gk {
+
+namespace {
+
+constexpr int TX = 32, TY = 8;
+
+struct c3 {
+    float x, y, z;
+};
+__device__ __forceinline__ c3 mk(float x, float y, float z) { return c3{x, y, z}; }
+__device__ __forceinline__ c3 operator+(c3 a, c3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ c3 operator*(c3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ c3 operator*(c3 a, c3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ c3 operator/(c3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ c3 mix3(c3 a, c3 b, float t) { return mk(mixf(a.x, b.x, t), mixf(a.y, b.y, t), mixf(a.z, b.z, t)); }
+__device__ __forceinline__ c3 min3(c3 a, c3 b) { return mk(fminx(a.x, b.x), fminx(a.y, b.y), fminx(a.z, b.z)); }
+__device__ __forceinline__ c3 max3(c3 a, c3 b) { return mk(fmaxx(a.x, b.x), fmaxx(a.y, b.y), fmaxx(a.z, b.z)); }
+__device__ __forceinline__ c3 clamp3(c3 v, c3 lo, c3 hi) { return min3(max3(v, lo), hi); }
+__device__ __forceinline__ c3 rgb2ycocg(c3 c) { return mk(0.25f * c.x + 0.5f * c.y + 0.25f * c.z, 0.5f * c.x - 0.5f * c.z, -0.25f * c.x + 0.5f * c.y - 0.25f * c.z); }
+__device__ __forceinline__ c3 ycocg2rgb(c3 c) { return mk(c.x + c.y - c.z, c.x + c.z, c.x - c.y - c.z); }
+
+__device__ __forceinline__ uint2 loadPx(const uint2* img, int x, int y, int W, int H)
+{
+    if (x < 0 || y < 0 || x >= W || y >= H) return make_uint2(0u, 0u);
+    return __ldg(img + (size_t)y * W + x);
+}
+__device__ __forceinline__ c3 unpackRgb(uint2 v)
+{
+    const __half2 a = *reinterpret_cast<const __half2*>(&v.x), b = *reinterpret_cast<const __half2*>(&v.y);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    return mk(fa.x, fa.y, fb.x);
+}
+__device__ __forceinline__ uint2 packRgba(c3 c, float a)
+{
+    const __half2 lo = __floats2half2_rn(c.x, c.y), hi = __floats2half2_rn(c.z, a);
+    uint2 v;
+    v.x = *reinterpret_cast<const uint32_t*>(&lo), v.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return v;
+}
+__device__ __forceinline__ uint32_t loadId(const uint32_t* img, int x, int y, int W, int H)
+{
+    if (x < 0 || y < 0 || x >= W || y >= H) return 0u;
+    return __ldg(img + (size_t)y * W + x);
+}
+
+__device__ __forceinline__ float calculateWeight(float centerDist, bool sameObject, bool isCenter, c3 n, c3 cn) // ReProject:40-55
+{
+    if (isCenter) return 0.4f;
+    if (!sameObject) return 0.0f;
+    const float nd = clampx(n.x * cn.x + n.y * cn.y + n.z * cn.z, 0.0f, 1.0f);
+    const float th = 0.98f;
+    if (nd < th) return 0.0f;
+    const float nw = (nd - th) / (1.0f - th);
+    return nw * 2.0f / (centerDist * 1.5f + 4.0f);
+}
+
+struct ReprojectArgs {
+    const uint2* src[3];   // rtOutputDiffuse, rtOutputSpecular, rtAlbedo_
+    const uint2* hist[3];  // rtPingPong0/1/3
+    uint2* out[3];         // rtAccumlatedDiffuse/Specular/Albedo_
+    const float2* motion;
+    const uint32_t* id0;
+    const uint32_t* id1;
+    const uint2* normal;
+    int W, H;
+};
+
+constexpr int RH = 2; // halo of the 5x5 windows
+constexpr int RW = TX + 2 * RH, RHT = TY + 2 * RH;
+
+__global__ void __launch_bounds__(TX* TY) k_reproject(const GkUniformBufferObject* __restrict__ ubo, ReprojectArgs A)
+{
+    __shared__ uint2 sSrc[3][RHT][RW];
+    __shared__ uint2 sNrm[RHT][RW];
+    __shared__ uint32_t sId[RHT][RW];
+    const GkUniformBufferObject& U = *ubo;
+    const int W = A.W, H = A.H;
+    const int vx = (int)U.ViewportRect[0], vy = (int)U.ViewportRect[1];
+    const int bx = blockIdx.x * TX + vx, by = blockIdx.y * TY + vy;
+    const bool progressive = U.ProgressiveRender != 0;
+    if (!progressive) {
+        for (int i = threadIdx.y * TX + threadIdx.x; i < RW * RHT; i += TX * TY) {
+            const int ly = i / RW, lx = i - ly * RW;
+            const int gx = bx + lx - RH, gy = by + ly - RH;
+            sSrc[0][ly][lx] = loadPx(A.src[0], gx, gy, W, H);
+            sSrc[1][ly][lx] = loadPx(A.src[1], gx, gy, W, H);
+            sSrc[2][ly][lx] = loadPx(A.src[2], gx, gy, W, H);
+            sNrm[ly][lx] = loadPx(A.normal, gx, gy, W, H);
+            sId[ly][lx] = loadId(A.id0, gx, gy, W, H);
+        }
+        __syncthreads();
+    }
+    const int x = bx + threadIdx.x, y = by + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t pi = (size_t)y * W + x;
+    if (progressive) { // ReProject:76-82
+        const float t = clampx(1.0f / float(U.TemporalFrames), 0.0f, 1.0f);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const c3 s = unpackRgb(__ldg(A.src[ch] + pi)), h = unpackRgb(__ldg(A.hist[ch] + pi));
+            A.out[ch][pi] = packRgba(mix3(h, s, t), 1.0f);
+        }
+        return;
+    }
+    const int lx = threadIdx.x + RH, ly = threadIdx.y + RH;
+    const float2 motion = __ldg(A.motion + pi);
+    const float fxp = float(x) + motion.x, fyp = float(y) + motion.y;
+    const int px = (int)floorf(fxp), py = (int)floorf(fyp);
+    const int vEndX = (int)(U.ViewportRect[0] + U.ViewportRect[2]), vEndY = (int)(U.ViewportRect[1] + U.ViewportRect[3]);
+    const bool inside = (px < vEndX && py < vEndY) && (px >= vx - 1 && py >= vy - 1);
+    const uint32_t cur0 = sId[ly][lx];
+    const bool useHistory = !(cur0 == 65535u || U.TotalFrames == 0 || !inside);
+    if (!useHistory) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) A.out[ch][pi] = packRgba(unpackRgb(sSrc[ch][ly][lx]), 1.0f);
+        return;
+    }
+    // spatial fallback weights are shared by the three channel sets (ReProject:93-121)
+    const int R = U.DisableSpatialReuse ? 0 : 2;
+    const c3 cn = unpackRgb(sNrm[ly][lx]);
+    float w[25];
+    float total = 0.f;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) {
+            float wt = 0.f;
+            if (dx >= -R && dx <= R && dy >= -R && dy <= R) {
+                const float cd = sqrtf(float(dx) * float(dx) + float(dy) * float(dy));
+                wt = calculateWeight(cd, sId[ly + dy][lx + dx] == cur0, dx == 0 && dy == 0, unpackRgb(sNrm[ly + dy][lx + dx]), cn);
+                total += wt;
+            }
+            w[(dy + 2) * 5 + dx + 2] = wt;
+        }
+    uint32_t p0 = loadId(A.id1, px, py, W, H), p1 = loadId(A.id1, px + 1, py, W, H), p2 = loadId(A.id1, px, py + 1, W, H), p3 = loadId(A.id1, px + 1, py + 1, W, H);
+    if (sqrtf(motion.x * motion.x + motion.y * motion.y) < 0.02f) p0 = p1 = p2 = p3 = cur0;
+    const float sx = fxp - floorf(fxp), sy = fyp - floorf(fyp);
+    const uint32_t tf = U.TemporalFrames > 1 ? U.TemporalFrames : 1;
+    const float keep = clampx(1.0f / float(tf), 0.0f, 1.0f);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const bool needClamp = (ch == 2); // PathTracingRenderer.cpp:122,131,139
+        c3 spatial = mk(0, 0, 0);
+        c3 mn = mk(0, 0, 0), mx = mk(0, 0, 0);
+        const c3 src = unpackRgb(sSrc[ch][ly][lx]);
+        if (needClamp) mn = mx = rgb2ycocg(src);
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                const c3 s = unpackRgb(sSrc[ch][ly + dy][lx + dx]);
+                if (dx >= -R && dx <= R && dy >= -R && dy <= R) spatial = spatial + s * w[(dy + 2) * 5 + dx + 2];
+                if (needClamp) {
+                    const c3 yc = rgb2ycocg(s);
+                    mn = min3(mn, yc), mx = max3(mx, yc);
+                }
+            }
+        spatial = spatial / total;
+        const c3 h0 = cur0 == p0 ? unpackRgb(loadPx(A.hist[ch], px, py, W, H)) : spatial;
+        const c3 h1 = cur0 == p1 ? unpackRgb(loadPx(A.hist[ch], px + 1, py, W, H)) : spatial;
+        const c3 h2 = cur0 == p2 ? unpackRgb(loadPx(A.hist[ch], px, py + 1, W, H)) : spatial;
+        const c3 h3 = cur0 == p3 ? unpackRgb(loadPx(A.hist[ch], px + 1, py + 1, W, H)) : spatial;
+        c3 history = mix3(mix3(h0, h1, sx), mix3(h2, h3, sx), sy);
+        history = clamp3(history, mk(0.f, 0.f, 0.f), mk(1600.f, 1600.f, 1600.f));
+        if (needClamp) history = ycocg2rgb(clamp3(rgb2ycocg(history), mn, mx));
+        A.out[ch][pi] = packRgba(mix3(history, src, keep), 1.0f);
+    }
+}
+
+// ---- tonemappers (Const_Func.slang:51-68, 84-126) ----
+__device__ __forceinline__ float W_f(float x, float e0, float e1)
+{
+    if (x <= e0) return 0;
+    if (x >= e1) return 1;
+    const float a = (x - e0) / (e1 - e0);
+    return a * a * (3 - 2 * a);
+}
+__device__ __forceinline__ float H_f(float x, float e0, float e1)
+{
+    if (x <= e0) return 0;
+    if (x >= e1) return 1;
+    return (x - e0) / (e1 - e0);
+}
+__device__ __forceinline__ float granTurismo(float x)
+{
+    const float e = 2.71828f;
+    const float P = 1, a = 0.7f, m = 0.22f, l = 0.4f, c = 1.33f, b = 0;
+    const float l0 = (P - m) * l / a;
+    const float L_x = m + a * (x - m);
+    const float T_x = m * powf(x / m, c) + b;
+    const float S0 = m + l0;
+    const float S1 = m + a * l0;
+    const float C2 = a * P / (P - S1);
+    const float S_x = P - (P - S1) * powf(e, -(C2 * (x - S0) / P));
+    const float w0 = 1 - W_f(x, 0, m);
+    const float w2 = H_f(x, m + l0, m + l0);
+    const float w1 = 1 - w0 - w2;
+    return T_x * w0 + L_x * w1 + S_x * w2;
+}
+__device__ __forceinline__ c3 gt3(c3 v) { return mk(granTurismo(v.x), granTurismo(v.y), granTurismo(v.z)); }
+__device__ __forceinline__ float st2084one(float v)
+{
+    const float m1 = 0.1593017578125f, m2 = 78.84375f, c1 = 0.8359375f, c2 = 18.8515625f, c3_ = 18.6875f, C = 10000.f;
+    const float L = v / C;
+    const float Lm = powf(L, m1);
+    const float N1 = c1 + c2 * Lm, N2 = 1.0f + c3_ * Lm;
+    const float N = N1 * (1.0f / N2);
+    return powf(N, m2);
+}
+
+__device__ __forceinline__ bool edgeDetect(uint32_t center, const uint32_t* img, int x, int y, int W, int H) // DenoiseJBF:55-68
+{
+    const uint32_t a = loadId(img, x + 1, y + 1, W, H), b = loadId(img, x - 1, y - 1, W, H), c = loadId(img, x - 1, y + 1, W, H), d = loadId(img, x + 1, y - 1, W, H);
+    const bool e0 = a != center || b != center || c != center || d != center;
+    const bool e1 = a == center || b == center || c == center || d == center;
+    return e0 && e1;
+}
+
+struct DenoiseArgs {
+    const uint2* diffuse; // rtAccumlatedDiffuse ("FinalImage")
+    const uint2* spec;    // rtAccumlatedSpecular
+    const uint2* albedo;  // rtAccumlatedAlbedo_
+    const uint32_t* id0;
+    const uint32_t* id1;
+    uint2* out; // rtDenoised
+    int W, H;
+};
+
+constexpr int DH = 5;
+constexpr int DW = TX + 2 * DH, DHT = TY + 2 * DH;
+
+__global__ void __launch_bounds__(TX* TY) k_denoise_jbf(const GkUniformBufferObject* __restrict__ ubo, DenoiseArgs A)
+{
+    __shared__ uint2 sDif[DHT][DW];
+    const GkUniformBufferObject& U = *ubo;
+    const int W = A.W, H = A.H;
+    const int vx = (int)U.ViewportRect[0], vy = (int)U.ViewportRect[1];
+    const int bx = blockIdx.x * TX + vx, by = blockIdx.y * TY + vy;
+    const bool filter = U.BFSize > 0;
+    if (filter) {
+        for (int i = threadIdx.y * TX + threadIdx.x; i < DW * DHT; i += TX * TY) {
+            const int ly = i / DW, lx = i - ly * DW;
+            sDif[ly][lx] = loadPx(A.diffuse, bx + lx - DH, by + ly - DH, W, H);
+        }
+        __syncthreads();
+    }
+    const int x = bx + threadIdx.x, y = by + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t pi = (size_t)y * W + x;
+    const c3 lumW = mk(0.212671f, 0.715160f, 0.072169f);
+    const c3 bias = mk(0.001f, 0.001f, 0.001f);
+    c3 Total = mk(0, 0, 0);
+    const c3 specC = unpackRgb(__ldg(A.spec + pi)), albC = unpackRgb(__ldg(A.albedo + pi));
+    if (filter) {
+        const int lx = threadIdx.x + DH, ly = threadIdx.y + DH;
+        const float sigma = U.BFSigma, sigmaL = U.BFSigmaLum * 100.0f;
+        const c3 cc = unpackRgb(sDif[ly][lx]) + bias;
+        const c3 cs = specC + bias;
+        const float clum = cc.x * lumW.x + cc.y * lumW.y + cc.z * lumW.z;
+        float Weight = 0;
+#pragma unroll
+        for (int i = -5; i <= 5; i += 2)
+#pragma unroll
+            for (int j = -5; j <= 5; j += 2) {
+                const c3 Ci = unpackRgb(sDif[ly + i][lx + j]) + bias;
+                const float lumi = Ci.x * lumW.x + Ci.y * lumW.y + Ci.z * lumW.z;
+                const float dist = clampx(float(i * i + j * j) / float(5 * 5), 0.0f, 1.0f);
+                const float dl = (clum - lumi) * (clum - lumi);
+                const float Fi = expf(-dist * dist / (2.0f * sigma * sigma));
+                const float Li = expf(-dl * dl / (2.0f * sigmaL * sigmaL));
+                Total = Total + Ci * Fi * Li;
+                Weight += Fi * Li;
+            }
+        Total = Total / Weight;
+        if (!U.DebugDraw_Lighting) Total = Total * albC + cs;
+    } else {
+        const c3 d = unpackRgb(__ldg(A.diffuse + pi));
+        if (U.DebugDraw_Lighting) Total = d * mk(0.5f, 0.5f, 0.5f) + specC;
+        else Total = d * albC + specC;
+    }
+    const float eThis = edgeDetect(U.SelectedId, A.id0, x, y, W, H) ? 0.5f : 0.0f;
+    const float ePrev = edgeDetect(U.SelectedId, A.id1, x, y, W, H) ? 0.5f : 0.0f;
+    if (eThis + eThis > 0) Total = mix3(Total, mk(150, 100, 0), eThis + ePrev);
+    c3 o;
+    if (U.HDR) {
+        Total = Total / 2000.f;
+        Total = gt3(Total);
+        Total = Total * 2000.f;
+        const c3 v = Total * U.PaperWhiteNit / 230.0f;
+        o = mk(st2084one(v.x), st2084one(v.y), st2084one(v.z));
+    } else {
+        o = gt3(Total * U.PaperWhiteNit / 40000.0f);
+    }
+    A.out[pi] = packRgba(o, 1.0f);
+}
+
+} // namespace
+
+GkStatus filterFrame(Context& c)
+{
+    if (!c.haveUbo) {
+        setLastError("gk_filter_frame: UBO must be set first");
+        return GK_ERR_NOT_READY;
+    }
+    cudaStream_t st = c.stream;
+    if (!c.tracedSinceFilter) applyPendingHistorySwap(c); // filter-only use: each call is a new frame
+    c.tracedSinceFilter = false;
+    GK_CUDA(cudaMemcpyAsync(c.dUbo, &c.ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventCreate(&e2);
+    void** P = c.planes.p;
+    ReprojectArgs R;
+    R.src[0] = (const uint2*)P[GK_PLANE_OUTPUT_DIFFUSE], R.src[1] = (const uint2*)P[GK_PLANE_OUTPUT_SPECULAR], R.src[2] = (const uint2*)P[GK_PLANE_ALBEDO];
+    R.hist[0] = (const uint2*)P[GK_PLANE_HISTORY_DIFFUSE], R.hist[1] = (const uint2*)P[GK_PLANE_HISTORY_SPECULAR], R.hist[2] = (const uint2*)P[GK_PLANE_HISTORY_ALBEDO];
+    R.out[0] = (uint2*)P[GK_PLANE_ACCUM_DIFFUSE], R.out[1] = (uint2*)P[GK_PLANE_ACCUM_SPECULAR], R.out[2] = (uint2*)P[GK_PLANE_ACCUM_ALBEDO];
+    R.motion = (const float2*)P[GK_PLANE_MOTION], R.id0 = (const uint32_t*)P[GK_PLANE_OBJECT_ID0], R.id1 = (const uint32_t*)P[GK_PLANE_OBJECT_ID1];
+    R.normal = (const uint2*)P[GK_PLANE_NORMAL];
+    R.W = (int)c.width, R.H = (int)c.height;
+    const dim3 block(TX, TY), grid((c.width + TX - 1) / TX, (c.height + TY - 1) / TY);
+    cudaEventRecord(e0, st);
+    k_reproject<<<grid, block, 0, st>>>(c.dUbo, R);
+    cudaEventRecord(e1, st);
+    DenoiseArgs D;
+    D.diffuse = R.out[0], D.spec = R.out[1], D.albedo = R.out[2], D.id0 = R.id0, D.id1 = R.id1, D.out = (uint2*)P[GK_PLANE_DENOISED];
+    D.W = R.W, D.H = R.H;
+    k_denoise_jbf<<<grid, block, 0, st>>>(c.dUbo, D);
+    cudaEventRecord(e2, st);
+    GK_CUDA(cudaGetLastError());
+    GK_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c.stats.msReproject, e0, e1);
+    cudaEventElapsedTime(&c.stats.msDenoise, e1, e2);
+    cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2);
+    c.stats.launches += 2;
+    // "copy pass": the accumulated images become next frame's history and ObjectId0 becomes
+    // ObjectId1.  No bytes move: the plane pointers are exchanged when the next frame starts
+    // (applyPendingHistorySwap); until then reads of the history planes resolve to the
+    // accumulated ones, which is what the reference's images hold after its copies.
+    c.pendingHistorySwap = true;
+    return GK_OK;
+}
+
+void applyPendingHistorySwap(Context& c)
+{
+    if (!c.pendingHistorySwap) return;
+    void** P = c.planes.p;
+    std::swap(P[GK_PLANE_ACCUM_DIFFUSE], P[GK_PLANE_HISTORY_DIFFUSE]);
+    std::swap(P[GK_PLANE_ACCUM_SPECULAR], P[GK_PLANE_HISTORY_SPECULAR]);
+    std::swap(P[GK_PLANE_ACCUM_ALBEDO], P[GK_PLANE_HISTORY_ALBEDO]);
+    std::swap(P[GK_PLANE_OBJECT_ID0], P[GK_PLANE_OBJECT_ID1]);
+    c.pendingHistorySwap = false;
+}
+
+} // namespace gk

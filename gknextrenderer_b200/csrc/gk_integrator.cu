@@ -1,0 +1,837 @@
+// gk_integrator.cu — the wavefront path tracer: generate / extend / shadow / shade / accumulate.
+//
+// Replaces Core.PathTracing.comp.slang (assets/shaders/Core.PathTracing.comp.slang:31-102) and the
+// megakernel it calls (FPathTracingRenderer, assets/shaders/common/Shading.slang:930-1082), which
+// the reference dispatches as 8x8 groups over the render extent
+// (src/Rendering/PathTracing/PathTracingRenderer.cpp:104-114).
+//
+// The megakernel's per-pixel program is cut at every ray cast into a small state machine; one
+// path per pixel walks it and carries the pcg4d state, so random numbers are drawn in exactly
+// the reference's per-pixel order (including the data-dependent draws):
+//
+//   generate : camera ray per owned pixel                      -> extend queue
+//   extend   : closest hit over TLAS/BLAS (gk_bvh.cuh)          -> hit records
+//   shadow   : any hit (sun next-event estimation, direct sun)  -> occlusion flags
+//   shade    : consumes hit / occlusion records, evaluates the material, draws the next
+//              direction or the NEE sample and appends to the extend / shadow queue of the next
+//              wave with one warp-aggregated atomic per warp (ballot + popc ranks)
+//   accumulate: writes the finished pixel to the RGBA16F planes (+ fp32 parity planes)
+//
+// Queues are SoA (origin|tmin, direction|tmax, path id; t|u|v|prim, instance), 32 + 4 + 20 bytes
+// per ray.  All kernels are one thread per queue entry, 256 threads per block.
+#include "gk_context.h"
+#include "gk_shading.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace gk {
+
+enum PathStateId : uint32_t { ST_PRIMARY = 0, ST_PRIMARY_DOF = 1, ST_BOUNCE = 2, ST_NEE = 3, ST_DIRECT = 4, ST_DONE = 5 };
+
+constexpr uint32_t F_CHANCE_REFLECT = 1u << 3, F_TERMINATE_ON_HIT = 1u << 4, F_HIT_REFLECT = 1u << 5, F_HIT_METAL = 1u << 6, F_PRIM_DIELECTRIC = 1u << 7,
+                   F_SRC_DIELECTRIC = 1u << 8;
+GK_HD uint32_t flagsState(uint32_t f) { return f & 7u; }
+GK_HD uint32_t flagsBounce(uint32_t f) { return (f >> 9) & 0x7fu; }
+GK_HD uint32_t flagsSample(uint32_t f) { return f >> 16; }
+GK_HD uint32_t packFlags(uint32_t state, uint32_t bits, uint32_t bounce, uint32_t sample) { return state | bits | (bounce << 9) | (sample << 16); }
+
+struct FrameParams {
+    uint32_t width, height;
+    uint32_t tileIndex, tileCount, tileRows;
+    uint32_t pathCount;
+};
+
+struct PlaneView {
+    __half* outDiffuse;
+    __half* outSpec;
+    __half* albedo;
+    __half* normal;
+    uint32_t* objectId0;
+    float2* motion;
+    float* depth;
+    float4* radDiffuse;
+    float4* radSpec;
+    uint2* primaryIds;
+    float* primaryT;
+    uint32_t* rayCount;
+};
+
+__device__ __forceinline__ void storeHalf4(__half* plane, uint32_t pixel, float x, float y, float z, float w)
+{
+    const __half2 a = __floats2half2_rn(x, y), b = __floats2half2_rn(z, w);
+    uint2 v;
+    v.x = *reinterpret_cast<const uint32_t*>(&a), v.y = *reinterpret_cast<const uint32_t*>(&b);
+    reinterpret_cast<uint2*>(plane)[pixel] = v;
+}
+
+__device__ __forceinline__ uint32_t pathToPixel(const FrameParams& P, uint32_t path)
+{
+    const uint32_t lr = path / P.width, x = path - lr * P.width;
+    const uint32_t blk = lr / P.tileRows, within = lr - blk * P.tileRows;
+    const uint32_t row = (blk * P.tileCount + P.tileIndex) * P.tileRows + within;
+    return row < P.height ? row * P.width + x : kInvalid;
+}
+
+__device__ __forceinline__ f3 cameraDir(const GkUniformBufferObject& U, int px, int py, uint32_t W, uint32_t H)
+{
+    const float ux = (float(px) / float(W)) * 2.0f - 1.0f, uy = (float(py) / float(H)) * 2.0f - 1.0f;
+    const f4 target = mulM(U.ProjectionInverse, mk4(ux, uy, 1, 1));
+    const f3 tn = normalize3(xyz(target));
+    const f4 dir = mulM(U.ModelViewInverse, mk4(tn.x, tn.y, tn.z, 0));
+    return normalize3(xyz(dir));
+}
+
+// -------------------------------------------------------------------------------- generate
+__global__ void __launch_bounds__(256) k_generate(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, PathState S, RayQueue Q)
+{
+    const uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= P.pathCount) return;
+    const GkUniformBufferObject& U = *ubo;
+    const uint32_t pixel = pathToPixel(P, path);
+    S.pixel[path] = pixel;
+    S.rays[path] = 0;
+    uint32_t x = 0, y = 0;
+    f3 dir = mk3(0, 0, 1);
+    const f3 origin = xyz(mulM(U.ModelViewInverse, mk4(0, 0, 0, 1)));
+    if (pixel != kInvalid) {
+        y = pixel / P.width, x = pixel - y * P.width;
+        dir = cameraDir(U, (int)x, (int)y, P.width, P.height);
+    }
+    S.rng[path] = make_uint4(x, y, U.TotalFrames, 0); // InitRandomSeed, Const_Func.slang:237-240
+    S.nrmFlags[path] = make_float4(0, 0, 0, __uint_as_float(packFlags(pixel == kInvalid ? ST_DONE : ST_PRIMARY, 0, 0, 0)));
+    S.accDiffuse[path] = make_float4(0, 0, 0, 0);
+    S.accSpec[path] = make_float4(0, 0, 0, 0);
+    // every path owns slot `path` of the first extend queue; rows past the image get a null ray
+    Q.o_tmin[path] = make_float4(origin.x, origin.y, origin.z, 0.0f);
+    Q.d_tmax[path] = make_float4(dir.x, dir.y, dir.z, pixel == kInvalid ? 0.0f : kPrimaryTMax);
+    Q.path[path] = path;
+    if (path == 0) *Q.count = P.pathCount;
+}
+
+// -------------------------------------------------------------------------------- extend / shadow
+template <bool kStats>
+__global__ void __launch_bounds__(256) k_extend(SceneView V, RayQueue Q, uint32_t count, TraversalStats* stats)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float4 o = Q.o_tmin[i], d = Q.d_tmax[i];
+    Hit h;
+    h.t = d.w, h.u = 0, h.v = 0, h.prim = kInvalid, h.inst = kInvalid;
+    TraversalStats local{0, 0};
+    if (d.w > 0.0f) {
+        const f3 dn = normalizeRayDir(mk3(d.x, d.y, d.z));
+        traverseScene<false, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, &local);
+    }
+    Q.hit_tuvp[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+    Q.hit_inst[i] = h.inst;
+    if (kStats) {
+        atomicAdd(&stats->nodeVisits, local.nodeVisits);
+        atomicAdd(&stats->triTests, local.triTests);
+    }
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(256) k_shadow(SceneView V, RayQueue Q, uint32_t count, TraversalStats* stats)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float4 o = Q.o_tmin[i], d = Q.d_tmax[i];
+    Hit h;
+    h.t = d.w, h.u = 0, h.v = 0, h.prim = kInvalid, h.inst = kInvalid;
+    TraversalStats local{0, 0};
+    const f3 dn = normalizeRayDir(mk3(d.x, d.y, d.z));
+    const bool occluded = traverseScene<true, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, &local);
+    Q.hit_inst[i] = occluded ? 1u : 0u;
+    if (kStats) {
+        atomicAdd(&stats->nodeVisits, local.nodeVisits);
+        atomicAdd(&stats->triTests, local.triTests);
+    }
+}
+
+// -------------------------------------------------------------------------------- shade
+struct Emit {
+    int kind; // 0 none, 1 extend, 2 shadow
+    f3 o, d;
+    float tmin, tmax;
+};
+
+// First half of GetRayColor (Shading.slang:934-965): draw the lobe, the direction, emit the ray.
+__device__ __forceinline__ void setupBounce(const ShadeScene& SS, u4& rng, const f3 pos, const f3 nrm, uint32_t matIdx, f3& dir, uint32_t& bits, bool firstBounce,
+                                            Emit& e)
+{
+    const GkMaterial& mat = SS.materials[matIdx];
+    const bool dielectric = mat.MaterialModel == GK_MAT_DIELECTRIC;
+    const float startPosOffset = dielectric ? 0.0f : 1.0f;
+    const float roughness = mat.Fuzziness;
+    const float dotValue = dot3(dir, nrm);
+    const bool backFace = dotValue > 0;
+    const f3 outwardNormal = backFace ? -nrm : nrm;
+    const float niOverNt = backFace ? mat.RefractionIndex2 : (1 / mat.RefractionIndex2);
+    const float cosine = dotValue > 0 ? mat.RefractionIndex * dotValue : -dotValue;
+    const float reflectProb = schlick(cosine, mat.RefractionIndex);
+    const float metalProb = mat.Metalness;
+    const bool chanceReflect = randomFloat(rng) < reflectProb;
+    const bool chanceMetal = randomFloat(rng) < metalProb;
+    const bool chanceGGX = chanceReflect || chanceMetal;
+    const f3 traceNext = chanceGGX ? reflect3(dir, outwardNormal) : outwardNormal;
+    f3 traceDir = chanceGGX ? ggxSampling(rng, sqrtf(roughness), traceNext) : alignWithNormal(randomInHemiSphere1(rng), traceNext);
+    if (dielectric && !chanceReflect) traceDir = refract3(dir, outwardNormal, niOverNt);
+    bits &= ~(F_CHANCE_REFLECT | F_TERMINATE_ON_HIT | F_SRC_DIELECTRIC);
+    if (chanceReflect) bits |= F_CHANCE_REFLECT;
+    if (backFace && !dielectric) bits |= F_TERMINATE_ON_HIT;
+    if (firstBounce) { // only the first GetRayColor of a sample reports its lobe (Shading.slang:1025 vs :1032)
+        bits &= ~(F_HIT_REFLECT | F_HIT_METAL);
+        if (chanceGGX) bits |= F_HIT_REFLECT;
+        if (chanceMetal) bits |= F_HIT_METAL;
+    }
+    dir = traceDir;
+    e.kind = 1;
+    e.o = pos + nrm * kTraceOffset * startPosOffset;
+    e.d = traceDir;
+    e.tmin = kEps, e.tmax = kMaxTrace;
+}
+
+__global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, ShadeScene SS, PathState S, PlaneView PL, RayQueue inE,
+                                               uint32_t countE, RayQueue inS, uint32_t countS, RayQueue outE, RayQueue outS)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < countE + countS;
+    Emit e;
+    e.kind = 0;
+    uint32_t path = 0;
+    if (active) {
+        const GkUniformBufferObject& U = *ubo;
+        const bool fromExtend = i < countE;
+        const uint32_t slot = fromExtend ? i : i - countE;
+        path = fromExtend ? inE.path[slot] : inS.path[slot];
+        const float4 nf = S.nrmFlags[path];
+        uint32_t flags = __float_as_uint(nf.w);
+        uint32_t state = flagsState(flags);
+        uint32_t bits = flags & (F_CHANCE_REFLECT | F_TERMINATE_ON_HIT | F_HIT_REFLECT | F_HIT_METAL | F_PRIM_DIELECTRIC | F_SRC_DIELECTRIC);
+        uint32_t bounce = flagsBounce(flags), sample = flagsSample(flags);
+        if (state != ST_DONE) {
+            const uint4 r4 = S.rng[path];
+            u4 rng{r4.x, r4.y, r4.z, r4.w};
+            const uint32_t pixel = S.pixel[path];
+            uint32_t rays = S.rays[path] + 1; // the ray whose result we are consuming
+            const f3 eye = xyz(mulM(U.ModelViewInverse, mk4(0, 0, 0, 1)));
+            const uint32_t samples = U.FastGather ? 1u : U.NumberOfSamples;
+
+            // working registers (loaded lazily per state)
+            f3 vpos = mk3(0, 0, 0), vnrm = mk3(nf.x, nf.y, nf.z), dir = mk3(0, 0, 0), color = mk3(1, 1, 1);
+            uint32_t vmat = 0;
+            f3 ppos = mk3(0, 0, 0), pnrm = mk3(0, 0, 0);
+            uint32_t pmat = 0;
+            float offLen = 0.f;
+            f3 accD = mk3(0, 0, 0), accS = mk3(0, 0, 0);
+            float shadowTerm = 0.f;
+            bool finished = false; // emissive primary: accD already holds the final value
+            bool accDirty = false;
+
+            enum Phase { PH_START_SAMPLE, PH_SETUP_BOUNCE, PH_POST_NEE, PH_END_SAMPLE, PH_AFTER_SAMPLES, PH_FINAL, PH_EXIT };
+            Phase phase = PH_EXIT;
+
+            auto loadPrimary = [&]() {
+                const float4 a = S.primPosMat[path], b = S.primNrm[path];
+                ppos = mk3(a.x, a.y, a.z), pmat = __float_as_uint(a.w);
+                pnrm = mk3(b.x, b.y, b.z), offLen = b.w;
+            };
+            auto loadAcc = [&]() {
+                const float4 a = S.accDiffuse[path], b = S.accSpec[path];
+                accD = mk3(a.x, a.y, a.z), accS = mk3(b.x, b.y, b.z);
+                accDirty = true;
+            };
+            auto loadCurrent = [&]() {
+                const float4 a = S.posMat[path], c = S.dirT[path], t = S.throughput[path];
+                vpos = mk3(a.x, a.y, a.z), vmat = __float_as_uint(a.w);
+                dir = mk3(c.x, c.y, c.z), color = mk3(t.x, t.y, t.z);
+            };
+
+            if (state == ST_PRIMARY || state == ST_PRIMARY_DOF) {
+                // ---- Core.PathTracing main :46-79 with FVisibilityBufferRayCaster (Shading.slang:287-434);
+                //      the visibility id comes from the traced primary ray instead of the raster pass.
+                const float4 hr = inE.hit_tuvp[slot];
+                const uint32_t hinst = inE.hit_inst[slot], hprim = __float_as_uint(hr.w);
+                const uint32_t py = pixel / P.width, px = pixel - py * P.width;
+                const f3 rayDir0 = cameraDir(U, (int)px, (int)py, P.width, P.height);
+                bool resolved = false;
+                Vtx hitV;
+                uint32_t hitNode = 0;
+                hitV.MaterialIndex = 0;
+                hitV.Position = hitV.Normal = mk3(0, 0, 0);
+                hitV.TexCoord = f2{0, 0};
+                if (state == ST_PRIMARY) {
+                    PL.primaryIds[pixel] = make_uint2(hinst == kInvalid ? kInvalid : hprim, hinst);
+                    PL.primaryT[pixel] = hr.x;
+                    if (hinst == kInvalid) {
+                        // miss: Core.PathTracing :53-64
+                        const f3 sky = skyColor(U);
+                        const float skyA = U.HasSky ? fminx(1.f, U.BackGroundColor[3]) * U.SkyIntensity : 0.f;
+                        PL.motion[pixel] = make_float2(0, 0);
+                        storeHalf4(PL.albedo, pixel, 1, 1, 1, 1);
+                        storeHalf4(PL.normal, pixel, 0, 1, 0, 1);
+                        PL.objectId0[pixel] = 65535u;
+                        PL.depth[pixel] = 0.f;
+                        S.accDiffuse[path] = make_float4(sky.x, sky.y, sky.z, skyA);
+                        S.accSpec[path] = make_float4(0, 0, 0, 0);
+                        state = ST_DONE;
+                    } else {
+                        uint32_t rawMat;
+                        const Vtx initial = getMaterialData(SS, hinst, hprim, eye, rayDir0, rawMat);
+                        const float vertexDistance = length3(initial.Position - eye);
+                        float coc = 0.0f;
+                        if (fabsf(vertexDistance - U.FocusDistance) > 0.001f) coc = (U.Aperture * fabsf(vertexDistance - U.FocusDistance)) / vertexDistance;
+                        float pox = 0.f, poy = 0.f;
+                        if (coc > 0.001f) {
+                            const f2 disk = concentricDisk(randomFloat2(rng));
+                            const f3 right = normalize3(cross3(rayDir0, mk3(0, 1, 0)));
+                            const f3 edge = initial.Position + right * coc;
+                            const f4 cp = mulM(U.ViewProjection, mk4(initial.Position.x, initial.Position.y, initial.Position.z, 1));
+                            const f4 ep = mulM(U.ViewProjection, mk4(edge.x, edge.y, edge.z, 1));
+                            const float dx = ep.x / ep.w - cp.x / cp.w, dy = ep.y / ep.w - cp.y / cp.w;
+                            const float ssr = sqrtf(dx * dx + dy * dy);
+                            pox = disk.x * ssr * float(P.width) * 0.5f, poy = disk.y * ssr * float(P.height) * 0.5f;
+                        }
+                        offLen = sqrtf(pox * pox + poy * poy);
+                        int ox = (int)px + (int)pox, oy = (int)py + (int)poy;
+                        ox = ox < 0 ? 0 : (ox > (int)P.width - 1 ? (int)P.width - 1 : ox);
+                        oy = oy < 0 ? 0 : (oy > (int)P.height - 1 ? (int)P.height - 1 : oy);
+                        if (ox == (int)px && oy == (int)py) {
+                            // the offset pixel is this pixel: its visibility id is the one we hold
+                            hitNode = hinst;
+                            hitV.Position = initial.Position, hitV.Normal = normalize3(initial.Normal), hitV.TexCoord = initial.TexCoord;
+                            hitV.MaterialIndex = SS.nodes[hinst].matId[rawMat & 15];
+                            resolved = true;
+                        } else {
+                            // depth of field: fetch the visibility id of the offset pixel by tracing its camera ray
+                            S.dofVertex[path] = make_float4(initial.Position.x, initial.Position.y, initial.Position.z, __uint_as_float(rawMat));
+                            S.dofNormal[path] = make_float4(initial.Normal.x, initial.Normal.y, initial.Normal.z, __uint_as_float(hinst));
+                            S.primNrm[path] = make_float4(__int_as_float(ox), __int_as_float(oy), vertexDistance, offLen);
+                            const f3 fd = cameraDir(U, ox, oy, P.width, P.height);
+                            e.kind = 1, e.o = eye, e.d = fd, e.tmin = 0.f, e.tmax = kPrimaryTMax;
+                            state = ST_PRIMARY_DOF;
+                        }
+                    }
+                } else {
+                    // ST_PRIMARY_DOF: Shading.slang:356-431
+                    const float4 dv = S.dofVertex[path], dn = S.dofNormal[path], aux = S.primNrm[path];
+                    const uint32_t rawMat0 = __float_as_uint(dv.w), node0 = __float_as_uint(dn.w);
+                    const int ox = __float_as_int(aux.x), oy = __float_as_int(aux.y);
+                    const float vertexDistance = aux.z;
+                    offLen = aux.w;
+                    bool useInitial = (hinst == kInvalid);
+                    Vtx finalV;
+                    uint32_t finalRaw = 0;
+                    if (!useInitial) {
+                        const f3 fd = cameraDir(U, ox, oy, P.width, P.height);
+                        finalV = getMaterialData(SS, hinst, hprim, eye, fd, finalRaw);
+                        if (fabsf(vertexDistance - U.FocusDistance) < U.FocusDistance * 0.1f) {
+                            const float fdist = length3(finalV.Position - eye);
+                            if (vertexDistance - fdist > U.FocusDistance * 0.05f) useInitial = true;
+                        }
+                    }
+                    if (useInitial) {
+                        hitNode = node0;
+                        hitV.Position = mk3(dv.x, dv.y, dv.z), hitV.Normal = normalize3(mk3(dn.x, dn.y, dn.z));
+                        hitV.MaterialIndex = SS.nodes[node0].matId[rawMat0 & 15];
+                    } else {
+                        hitNode = hinst;
+                        hitV.Position = finalV.Position, hitV.Normal = normalize3(finalV.Normal);
+                        hitV.MaterialIndex = SS.nodes[hinst].matId[finalRaw & 15];
+                    }
+                    resolved = true;
+                }
+                if (resolved) {
+                    const GkNodeProxy& hn = SS.nodes[hitNode];
+                    { // CalculateMotionVector, Shading.slang:50-58
+                        const f4 cur = mulM(U.ViewProjectionUnJit, mk4(hitV.Position.x, hitV.Position.y, hitV.Position.z, 1));
+                        const float cx = cur.x / cur.w * 0.5f, cy = cur.y / cur.w * 0.5f;
+                        float PM[16];
+                        for (int c = 0; c < 4; ++c)
+                            for (int r = 0; r < 4; ++r) {
+                                float s = 0;
+                                for (int k = 0; k < 4; ++k) s += U.PrevViewProjectionUnJit[k * 4 + r] * hn.combinedPrevTS[c * 4 + k];
+                                PM[c * 4 + r] = s;
+                            }
+                        const f4 prev = mulM(PM, mk4(hitV.Position.x, hitV.Position.y, hitV.Position.z, 1));
+                        const float qx = prev.x / prev.w * 0.5f, qy = prev.y / prev.w * 0.5f;
+                        PL.motion[pixel] = make_float2((qx - cx) * float(P.width), (qy - cy) * float(P.height));
+                    }
+                    const GkMaterial& mat = SS.materials[hitV.MaterialIndex];
+                    storeHalf4(PL.albedo, pixel, mat.Diffuse[0], mat.Diffuse[1], mat.Diffuse[2], mat.Diffuse[3]);
+                    storeHalf4(PL.normal, pixel, hitV.Normal.x, hitV.Normal.y, hitV.Normal.z, mat.Fuzziness);
+                    PL.objectId0[pixel] = hn.instanceId;
+                    {
+                        const f4 clip = mulM(U.ViewProjection, mk4(hitV.Position.x, hitV.Position.y, hitV.Position.z, 1));
+                        PL.depth[pixel] = clip.z / clip.w;
+                    }
+                    ppos = hitV.Position, pnrm = hitV.Normal, pmat = hitV.MaterialIndex;
+                    S.primPosMat[path] = make_float4(ppos.x, ppos.y, ppos.z, __uint_as_float(pmat));
+                    S.primNrm[path] = make_float4(pnrm.x, pnrm.y, pnrm.z, offLen);
+                    bits = (mat.MaterialModel == GK_MAT_DIELECTRIC) ? F_PRIM_DIELECTRIC : 0u;
+                    sample = 0;
+                    accDirty = true;
+                    if (mat.MaterialModel == GK_MAT_DIFFUSE_LIGHT) { // Shading.slang:1003-1008
+                        accD = mk3(mat.Diffuse[0], mat.Diffuse[1], mat.Diffuse[2]), accS = mk3(0, 0, 0);
+                        finished = true;
+                        phase = PH_FINAL;
+                    } else {
+                        phase = samples > 0 ? PH_START_SAMPLE : PH_AFTER_SAMPLES;
+                    }
+                }
+            } else if (state == ST_BOUNCE) {
+                // ---- second half of GetRayColor (Shading.slang:965-995)
+                loadPrimary();
+                loadAcc();
+                loadCurrent();
+                const float4 hr = inE.hit_tuvp[slot];
+                const uint32_t hinst = inE.hit_inst[slot];
+                const uint32_t maxBounces = (bits & F_PRIM_DIELECTRIC) ? U.MaxNumberOfBounces : U.NumberOfBounces;
+                bool terminated;
+                if (hinst != kInvalid) {
+                    const float4 ro = inE.o_tmin[slot], rd = inE.d_tmax[slot];
+                    Vtx hv;
+                    resolveHit(SS, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), hr.x, hr.y, hr.z, __float_as_uint(hr.w), hinst, hv);
+                    vpos = hv.Position, vnrm = hv.Normal, vmat = hv.MaterialIndex;
+                    const GkMaterial& hm = SS.materials[vmat];
+                    const bool light = hm.MaterialModel == GK_MAT_DIFFUSE_LIGHT;
+                    if (light || !(bits & F_CHANCE_REFLECT)) color = color * mk3(hm.Diffuse[0], hm.Diffuse[1], hm.Diffuse[2]);
+                    if (bits & F_TERMINATE_ON_HIT) {
+                        color = mk3(0, 0, 0);
+                        terminated = true;
+                    } else terminated = light;
+                } else {
+                    color = color * skyColor(U);
+                    terminated = true;
+                }
+                if (terminated) phase = PH_END_SAMPLE;
+                else if (bounce == 0) {
+                    bounce = 1;
+                    phase = (1u < maxBounces) ? PH_SETUP_BOUNCE : PH_END_SAMPLE;
+                } else {
+                    // sun next-event estimation, Shading.slang:1037-1046 (guard variable is never written: always taken)
+                    if (U.HasSun && (randomFloat(rng) < 0.5f)) {
+                        const f3 lv = mk3(U.SunDirection[0], U.SunDirection[1], U.SunDirection[2]);
+                        const f3 cone = alignWithNormal(randomInCone(rng, cosf(0.25f / 180.f * kPi)), lv);
+                        e.kind = 2, e.o = vpos + vnrm * kTraceOffset, e.d = cone, e.tmin = kEps, e.tmax = kMaxTrace;
+                        state = ST_NEE;
+                    } else phase = PH_POST_NEE;
+                }
+            } else if (state == ST_NEE) {
+                loadPrimary();
+                loadAcc();
+                loadCurrent();
+                const bool occluded = inS.hit_inst[slot] != 0;
+                if (!occluded) {
+                    color = color * mk3(U.SunColor[0], U.SunColor[1], U.SunColor[2]);
+                    phase = PH_END_SAMPLE;
+                } else phase = PH_POST_NEE;
+            } else if (state == ST_DIRECT) {
+                loadPrimary();
+                loadAcc();
+                shadowTerm = inS.hit_inst[slot] != 0 ? 0.f : 1.f;
+                phase = PH_FINAL;
+            }
+
+            // ---- run the control flow of FPathTracingRenderer::Render until the next ray (Shading.slang:1010-1081)
+            while (phase != PH_EXIT) {
+                const uint32_t maxBounces = (bits & F_PRIM_DIELECTRIC) ? U.MaxNumberOfBounces : U.NumberOfBounces;
+                switch (phase) {
+                case PH_START_SAMPLE:
+                    color = mk3(1, 1, 1);
+                    dir = normalize3(ppos - eye);
+                    vpos = ppos, vnrm = pnrm, vmat = pmat;
+                    bounce = 0;
+                    phase = PH_SETUP_BOUNCE;
+                    break;
+                case PH_SETUP_BOUNCE:
+                    setupBounce(SS, rng, vpos, vnrm, vmat, dir, bits, bounce == 0, e);
+                    state = ST_BOUNCE;
+                    phase = PH_EXIT;
+                    break;
+                case PH_POST_NEE: {
+                    // early exit, Shading.slang:1049-1056 (the random number is drawn only for non-dielectric primaries)
+                    const bool earlyExit = !(bits & F_PRIM_DIELECTRIC) && (randomFloat(rng) < 0.5f);
+                    if (bounce == maxBounces - 1 || earlyExit) {
+                        color = color * interpolateAmbientCubes(SS, vpos, vnrm);
+                        phase = PH_END_SAMPLE;
+                    } else {
+                        ++bounce;
+                        phase = PH_SETUP_BOUNCE;
+                    }
+                    break;
+                }
+                case PH_END_SAMPLE: {
+                    if (bits & F_HIT_METAL) {
+                        const GkMaterial& pm = SS.materials[pmat];
+                        color = color * mk3(pm.Diffuse[0], pm.Diffuse[1], pm.Diffuse[2]);
+                    }
+                    if (bits & F_HIT_REFLECT) accS = accS + color;
+                    else accD = accD + color;
+                    ++sample;
+                    phase = sample < samples ? PH_START_SAMPLE : PH_AFTER_SAMPLES;
+                    break;
+                }
+                case PH_AFTER_SAMPLES: {
+                    accD = accD / float(samples);
+                    accS = accS / float(samples);
+                    if (U.HasSun) { // DirectIlluminate, Shading.slang:826-845
+                        const f3 lv = mk3(U.SunDirection[0], U.SunDirection[1], U.SunDirection[2]);
+                        const f3 cone = alignWithNormal(randomInCone(rng, cosf(0.25f / 180.f * kPi)), lv);
+                        e.kind = 2, e.o = ppos, e.d = cone, e.tmin = kEps, e.tmax = kMaxTrace;
+                        state = ST_DIRECT;
+                        phase = PH_EXIT;
+                    } else {
+                        shadowTerm = 0.f;
+                        phase = PH_FINAL;
+                    }
+                    break;
+                }
+                case PH_FINAL: {
+                    if (!finished) {
+                        const f3 lv = mk3(U.SunDirection[0], U.SunDirection[1], U.SunDirection[2]);
+                        const float d = fmaxx(dot3(lv, normalize3(pnrm)), 0.0f) * kInvPi;
+                        accD = accD + mk3(U.SunColor[0], U.SunColor[1], U.SunColor[2]) * d * shadowTerm;
+                    }
+                    state = ST_DONE;
+                    phase = PH_EXIT;
+                    break;
+                }
+                default: phase = PH_EXIT; break;
+                }
+            }
+
+            // ---- write back
+            S.rng[path] = make_uint4(rng.x, rng.y, rng.z, rng.w);
+            S.rays[path] = rays;
+            if (state == ST_BOUNCE || state == ST_NEE) {
+                S.posMat[path] = make_float4(vpos.x, vpos.y, vpos.z, __uint_as_float(vmat));
+                S.dirT[path] = make_float4(dir.x, dir.y, dir.z, 0);
+                S.throughput[path] = make_float4(color.x, color.y, color.z, 0);
+            }
+            if (accDirty) {
+                S.accDiffuse[path] = make_float4(accD.x, accD.y, accD.z, offLen);
+                S.accSpec[path] = make_float4(accS.x, accS.y, accS.z, offLen);
+            }
+            S.nrmFlags[path] = make_float4(vnrm.x, vnrm.y, vnrm.z, __uint_as_float(packFlags(state, bits, bounce, sample)));
+        }
+    }
+
+    // ---- append to the next wave's queues: one atomic per warp and queue
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    {
+        const unsigned m = __ballot_sync(full, e.kind == 1);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(outE.count, (uint32_t)__popc(m));
+            base = __shfl_sync(full, base, __ffs(m) - 1);
+            if (e.kind == 1) {
+                const uint32_t dst = base + __popc(m & ((1u << lane) - 1u));
+                outE.o_tmin[dst] = make_float4(e.o.x, e.o.y, e.o.z, e.tmin);
+                outE.d_tmax[dst] = make_float4(e.d.x, e.d.y, e.d.z, e.tmax);
+                outE.path[dst] = path;
+            }
+        }
+    }
+    {
+        const unsigned m = __ballot_sync(full, e.kind == 2);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(outS.count, (uint32_t)__popc(m));
+            base = __shfl_sync(full, base, __ffs(m) - 1);
+            if (e.kind == 2) {
+                const uint32_t dst = base + __popc(m & ((1u << lane) - 1u));
+                outS.o_tmin[dst] = make_float4(e.o.x, e.o.y, e.o.z, e.tmin);
+                outS.d_tmax[dst] = make_float4(e.d.x, e.d.y, e.d.z, e.tmax);
+                outS.path[dst] = path;
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------- accumulate
+// Core.PathTracing :88-100 — final stores of the pixel (RGBA16F render targets + fp32 parity copies)
+__global__ void __launch_bounds__(256) k_accumulate(FrameParams P, PathState S, PlaneView PL)
+{
+    const uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= P.pathCount) return;
+    const uint32_t pixel = S.pixel[path];
+    if (pixel == kInvalid) return;
+    const float4 d = S.accDiffuse[path], s = S.accSpec[path];
+    PL.radDiffuse[pixel] = d;
+    PL.radSpec[pixel] = s;
+    storeHalf4(PL.outDiffuse, pixel, d.x, d.y, d.z, d.w);
+    storeHalf4(PL.outSpec, pixel, s.x, s.y, s.z, s.w);
+    PL.rayCount[pixel] = S.rays[path];
+}
+
+// -------------------------------------------------------------------------------- utilities
+template <bool kAny, bool kStats>
+__global__ void __launch_bounds__(256) k_intersect(SceneView V, const float4* __restrict__ rays, uint32_t n, float* __restrict__ tuv, uint32_t* __restrict__ ids,
+                                                   TraversalStats* stats)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = rays[2 * i], d = rays[2 * i + 1];
+    Hit h;
+    h.t = d.w, h.u = 0, h.v = 0, h.prim = kInvalid, h.inst = kInvalid;
+    TraversalStats local{0, 0};
+    const f3 dn = normalizeRayDir(mk3(d.x, d.y, d.z));
+    const bool hit = traverseScene<kAny, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, &local);
+    if (tuv) tuv[3 * i] = h.t, tuv[3 * i + 1] = h.u, tuv[3 * i + 2] = h.v;
+    if (ids) {
+        if (kAny) ids[2 * i] = hit ? 1u : 0u, ids[2 * i + 1] = hit ? 1u : 0u;
+        else ids[2 * i] = h.inst == kInvalid ? kInvalid : h.prim, ids[2 * i + 1] = h.inst;
+    }
+    if (kStats) {
+        atomicAdd(&stats->nodeVisits, local.nodeVisits);
+        atomicAdd(&stats->triTests, local.triTests);
+    }
+}
+
+// -------------------------------------------------------------------------------- host side
+static inline unsigned gridFor(size_t n, unsigned block = 256) { return (unsigned)((n + block - 1) / block); }
+
+template <class T> static cudaError_t allocInto(std::vector<void*>& pool, T*& p, size_t n)
+{
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e == cudaSuccess) {
+        pool.push_back(q);
+        p = reinterpret_cast<T*>(q);
+    }
+    return e;
+}
+
+void freeFrameResources(Context& c)
+{
+    for (void* p : c.pathAllocs) cudaFree(p);
+    for (void* p : c.queueAllocs) cudaFree(p);
+    c.pathAllocs.clear(), c.queueAllocs.clear();
+    for (int i = 0; i < GK_PLANE_COUNT; ++i) {
+        if (c.planes.p[i]) cudaFree(c.planes.p[i]);
+        c.planes.p[i] = nullptr, c.planes.bytes[i] = 0;
+    }
+    if (c.dUbo) cudaFree(c.dUbo);
+    c.dUbo = nullptr;
+    if (c.hCounts) cudaFreeHost(c.hCounts);
+    c.hCounts = nullptr;
+    if (c.dTravStats) cudaFree(c.dTravStats);
+    c.dTravStats = nullptr;
+}
+
+static size_t planePixelBytes(int plane)
+{
+    switch (plane) {
+    case GK_PLANE_OBJECT_ID0:
+    case GK_PLANE_OBJECT_ID1:
+    case GK_PLANE_DEPTH:
+    case GK_PLANE_PRIMARY_T:
+    case GK_PLANE_RAY_COUNT: return 4;
+    case GK_PLANE_RADIANCE_DIFFUSE_F32:
+    case GK_PLANE_RADIANCE_SPECULAR_F32: return 16;
+    default: return 8; // RGBA16F, RG32F, 2 x u32
+    }
+}
+
+GkStatus allocFrameResources(Context& c)
+{
+    freeFrameResources(c);
+    const size_t px = (size_t)c.width * c.height;
+    // owned rows of this rank's tile set
+    uint32_t owned = 0;
+    for (uint32_t r = 0; r < c.height; ++r)
+        if ((r / c.tileRows) % c.tileCount == c.tileIndex) ++owned;
+    // paths are laid out in whole tile-row blocks so that pathToPixel stays arithmetic
+    const uint32_t blocks = (c.height + c.tileRows * c.tileCount - 1) / (c.tileRows * c.tileCount);
+    c.ownedRows = owned;
+    c.pathCount = blocks * c.tileRows * c.width;
+    const size_t n = c.pathCount;
+    for (int i = 0; i < GK_PLANE_COUNT; ++i) {
+        c.planes.bytes[i] = px * planePixelBytes(i);
+        GK_CUDA(cudaMalloc(&c.planes.p[i], c.planes.bytes[i]));
+        GK_CUDA(cudaMemsetAsync(c.planes.p[i], 0, c.planes.bytes[i], c.stream));
+    }
+    PathState& S = c.paths;
+    GK_CUDA(allocInto(c.pathAllocs, S.rng, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.posMat, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.nrmFlags, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.dirT, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.throughput, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.primPosMat, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.primNrm, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.accDiffuse, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.accSpec, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.pixel, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.rays, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.dofVertex, n));
+    GK_CUDA(allocInto(c.pathAllocs, S.dofNormal, n));
+    for (int k = 0; k < 4; ++k) {
+        RayQueue& Q = k < 2 ? c.extendQ[k] : c.shadowQ[k - 2];
+        GK_CUDA(allocInto(c.queueAllocs, Q.o_tmin, n));
+        GK_CUDA(allocInto(c.queueAllocs, Q.d_tmax, n));
+        GK_CUDA(allocInto(c.queueAllocs, Q.path, n));
+        GK_CUDA(allocInto(c.queueAllocs, Q.hit_tuvp, n));
+        GK_CUDA(allocInto(c.queueAllocs, Q.hit_inst, n));
+        GK_CUDA(allocInto(c.queueAllocs, Q.count, 4));
+        GK_CUDA(cudaMemsetAsync(Q.count, 0, 16, c.stream));
+    }
+    GK_CUDA(cudaMalloc(&c.dUbo, sizeof(GkUniformBufferObject)));
+    GK_CUDA(cudaMallocHost(&c.hCounts, 64));
+    GK_CUDA(cudaMalloc(&c.dTravStats, sizeof(TraversalStats)));
+    GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    return GK_OK;
+}
+
+static ShadeScene shadeSceneOf(const Context& c)
+{
+    ShadeScene s;
+    s.verts = c.dGpuVerts.p, s.indices = c.dIndices.p, s.models = c.dModels.p, s.materials = c.dMaterials.p, s.nodes = c.dNodes.p, s.inst = c.dInst.p;
+    s.cubes = c.haveProbes ? c.dCubes.p : nullptr, s.voxels = c.haveProbes ? c.dVoxels.p : nullptr;
+    s.materialCount = c.materialCount;
+    return s;
+}
+
+static PlaneView planeViewOf(const Context& c)
+{
+    PlaneView v;
+    v.outDiffuse = (__half*)c.planes.p[GK_PLANE_OUTPUT_DIFFUSE], v.outSpec = (__half*)c.planes.p[GK_PLANE_OUTPUT_SPECULAR];
+    v.albedo = (__half*)c.planes.p[GK_PLANE_ALBEDO], v.normal = (__half*)c.planes.p[GK_PLANE_NORMAL];
+    v.objectId0 = (uint32_t*)c.planes.p[GK_PLANE_OBJECT_ID0], v.motion = (float2*)c.planes.p[GK_PLANE_MOTION], v.depth = (float*)c.planes.p[GK_PLANE_DEPTH];
+    v.radDiffuse = (float4*)c.planes.p[GK_PLANE_RADIANCE_DIFFUSE_F32], v.radSpec = (float4*)c.planes.p[GK_PLANE_RADIANCE_SPECULAR_F32];
+    v.primaryIds = (uint2*)c.planes.p[GK_PLANE_PRIMARY_IDS], v.primaryT = (float*)c.planes.p[GK_PLANE_PRIMARY_T], v.rayCount = (uint32_t*)c.planes.p[GK_PLANE_RAY_COUNT];
+    return v;
+}
+
+static cudaEvent_t poolEvent(Context& c, size_t i)
+{
+    while (c.evPool.size() <= i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c.evPool.push_back(e);
+    }
+    return c.evPool[i];
+}
+
+GkStatus traceFrame(Context& c)
+{
+    if (!c.haveScene || !c.haveInstances || !c.haveUbo) {
+        setLastError("gk_trace_frame: scene, instances and UBO must be set first");
+        return GK_ERR_NOT_READY;
+    }
+    cudaStream_t st = c.stream;
+    applyPendingHistorySwap(c);
+    c.tracedSinceFilter = true;
+    const uint32_t n = c.pathCount;
+    FrameParams P{c.width, c.height, c.tileIndex, c.tileCount, c.tileRows, n};
+    const SceneView V = c.view();
+    const ShadeScene SS = shadeSceneOf(c);
+    const PlaneView PL = planeViewOf(c);
+    GkFrameStats& fs = c.stats;
+    fs.primaryRays = fs.extensionRays = fs.shadowRays = 0;
+    fs.waves = fs.launches = 0;
+    fs.msGenerate = fs.msExtend = fs.msShade = fs.msShadow = fs.msAccumulate = 0;
+    size_t ev = 0;
+    struct Span { size_t a, b; int kind; };
+    std::vector<Span> spans;
+    auto mark = [&]() { cudaEvent_t e = poolEvent(c, ev); cudaEventRecord(e, st); return ev++; };
+
+    GK_CUDA(cudaMemcpyAsync(c.dUbo, &c.ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, st));
+    if (c.travStats) GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), st));
+    const size_t evStart = mark();
+    int cur = 0;
+    k_generate<<<gridFor(n), 256, 0, st>>>(c.dUbo, P, c.paths, c.extendQ[cur]);
+    fs.launches++;
+    GK_CUDA(cudaMemsetAsync(c.shadowQ[cur].count, 0, sizeof(uint32_t), st));
+    const size_t evGen = mark();
+    spans.push_back({evStart, evGen, 0});
+    uint32_t countE = n, countS = 0;
+    fs.primaryRays = (uint64_t)c.ownedRows * c.width;
+    c.capturedCount = 0;
+    for (uint32_t wave = 0; wave < 4096; ++wave) {
+        if (countE == 0 && countS == 0) break;
+        const size_t a = mark();
+        if (countE) {
+            if ((int)wave == c.captureWave) {
+                GK_CUDA(c.dCapture.reserve(2 * (size_t)countE));
+                // interleave origin/direction records for the CPU baseline
+                GK_CUDA(cudaMemcpy2DAsync(c.dCapture.p, 32, c.extendQ[cur].o_tmin, 16, 16, countE, cudaMemcpyDeviceToDevice, st));
+                GK_CUDA(cudaMemcpy2DAsync(c.dCapture.p + 1, 32, c.extendQ[cur].d_tmax, 16, 16, countE, cudaMemcpyDeviceToDevice, st));
+                c.capturedCount = countE;
+            }
+            if (c.travStats) k_extend<true><<<gridFor(countE), 256, 0, st>>>(V, c.extendQ[cur], countE, c.dTravStats);
+            else k_extend<false><<<gridFor(countE), 256, 0, st>>>(V, c.extendQ[cur], countE, nullptr);
+            fs.launches++;
+        }
+        const size_t b = mark();
+        if (countS) {
+            if (c.travStats) k_shadow<true><<<gridFor(countS), 256, 0, st>>>(V, c.shadowQ[cur], countS, c.dTravStats);
+            else k_shadow<false><<<gridFor(countS), 256, 0, st>>>(V, c.shadowQ[cur], countS, nullptr);
+            fs.launches++;
+        }
+        const size_t d = mark();
+        const int nxt = cur ^ 1;
+        GK_CUDA(cudaMemsetAsync(c.extendQ[nxt].count, 0, sizeof(uint32_t), st));
+        GK_CUDA(cudaMemsetAsync(c.shadowQ[nxt].count, 0, sizeof(uint32_t), st));
+        k_shade<<<gridFor((size_t)countE + countS), 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.extendQ[nxt],
+                                                              c.shadowQ[nxt]);
+        fs.launches++;
+        const size_t f = mark();
+        spans.push_back({a, b, 1}), spans.push_back({b, d, 2}), spans.push_back({d, f, 3});
+        GK_CUDA(cudaMemcpyAsync(c.hCounts, c.extendQ[nxt].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaMemcpyAsync(c.hCounts + 1, c.shadowQ[nxt].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        if (wave > 0) fs.extensionRays += countE;
+        fs.shadowRays += countS;
+        countE = c.hCounts[0], countS = c.hCounts[1];
+        fs.waves++;
+        cur = nxt;
+    }
+    const size_t g = mark();
+    k_accumulate<<<gridFor(n), 256, 0, st>>>(P, c.paths, PL);
+    fs.launches++;
+    const size_t hEnd = mark();
+    spans.push_back({g, hEnd, 4});
+    GK_CUDA(cudaGetLastError());
+    GK_CUDA(cudaStreamSynchronize(st));
+    for (const Span& s : spans) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.evPool[s.a], c.evPool[s.b]);
+        if (s.kind == 0) fs.msGenerate += ms;
+        else if (s.kind == 1) fs.msExtend += ms;
+        else if (s.kind == 2) fs.msShadow += ms;
+        else if (s.kind == 3) fs.msShade += ms;
+        else fs.msAccumulate += ms;
+    }
+    cudaEventElapsedTime(&fs.msTotal, c.evPool[evStart], c.evPool[hEnd]);
+    if (c.travStats) {
+        TraversalStats h;
+        GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));
+        fs.nodeVisits = h.nodeVisits, fs.triTests = h.triTests;
+    }
+    return GK_OK;
+}
+
+GkStatus intersectDevice(Context& c, const float4* rays, uint32_t n, float* tuv, uint32_t* ids, bool anyHit)
+{
+    if (!c.haveScene || !c.haveInstances) {
+        setLastError("gk_intersect: scene and instances must be set first");
+        return GK_ERR_NOT_READY;
+    }
+    if (n == 0) return GK_OK;
+    const SceneView V = c.view();
+    if (c.travStats) {
+        if (anyHit) k_intersect<true, true><<<gridFor(n), 256, 0, c.stream>>>(V, rays, n, tuv, ids, c.dTravStats);
+        else k_intersect<false, true><<<gridFor(n), 256, 0, c.stream>>>(V, rays, n, tuv, ids, c.dTravStats);
+    } else {
+        if (anyHit) k_intersect<true, false><<<gridFor(n), 256, 0, c.stream>>>(V, rays, n, tuv, ids, nullptr);
+        else k_intersect<false, false><<<gridFor(n), 256, 0, c.stream>>>(V, rays, n, tuv, ids, nullptr);
+    }
+    GK_CUDA(cudaGetLastError());
+    return GK_OK;
+}
+
+} // namespace gk

@@ -1,0 +1,180 @@
+/*
+ * gknext_cuda.h — C ABI of the B200 (sm_100a) CUDA backend for gkNextRenderer's
+ * path-tracing hot path.  This is the drop-in boundary: a logic renderer registered behind
+ * the reference's renderer switch forwards its five virtuals to these entry points
+ * (INTEGRATION.md shows the shim).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every call returns GK_OK (0) or a negative GkStatus; gk_last_error() gives the text.
+ *     Nothing throws across this boundary (the reference throws C++ exceptions,
+ *     src/Utilities/Exception.hpp:10-16; the shim converts).
+ *   - one caller thread per context (the reference drives its renderer from the main thread,
+ *     src/Rendering/VulkanBaseRenderer.cpp:889-1030).  Calls enqueue work on the context's
+ *     CUDA stream; gk_readback / gk_synchronize / gk_get_stats wait for it.
+ *   - the caller keeps ownership of every host pointer; the backend copies during the call
+ *     (the reference frees its CPU vertex arrays right after upload, src/Assets/Scene.cpp:195).
+ *   - there is no CPU fallback: every entry point fails with GK_ERR_CUDA if no sm_100 device
+ *     is usable.
+ */
+#ifndef GKNEXT_CUDA_H_
+#define GKNEXT_CUDA_H_
+
+#include "gknext_types.h"
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GK_ABI_VERSION 1
+
+typedef enum GkStatus {
+    GK_OK = 0,
+    GK_ERR_INVALID_ARGUMENT = -1,
+    GK_ERR_CUDA = -2,
+    GK_ERR_OUT_OF_MEMORY = -3,
+    GK_ERR_NOT_READY = -4, /* e.g. render before a scene/instances/UBO were supplied */
+    GK_ERR_UNSUPPORTED = -5
+} GkStatus;
+
+typedef struct GkContext GkContext;
+
+typedef struct GkConfig {
+    int32_t device;          /* CUDA ordinal, -1 = current device */
+    uint32_t width, height;  /* render extent (SwapChain().RenderExtent()) */
+    /* Multi-GPU frame partition.  With tileCount > 1 this context traces only
+     * the image rows r with (r / tileRows) % tileCount == tileIndex; the other rows of the
+     * path-tracer output planes are left untouched for the frame-end exchange. */
+    uint32_t tileIndex, tileCount, tileRows;
+    uint32_t flags;          /* GkConfigFlags */
+    uint32_t reserved[6];
+} GkConfig;
+
+enum GkConfigFlags {
+    GK_CFG_DEFAULT = 0,
+    GK_CFG_BVH2_TRAVERSAL = 1u << 0 /* debug: traverse the binary LBVH instead of the 8-wide nodes */
+};
+
+/* Image planes, named after the reference's render targets
+ * (src/Rendering/VulkanBaseRenderer.cpp:488-543, bindings :571-584). */
+typedef enum GkPlane {
+    GK_PLANE_OUTPUT_DIFFUSE = 0,   /* rtOutputDiffuse     RGBA16F  8 B/px */
+    GK_PLANE_OUTPUT_SPECULAR = 1,  /* rtOutputSpecular    RGBA16F */
+    GK_PLANE_ALBEDO = 2,           /* rtAlbedo_           RGBA16F */
+    GK_PLANE_NORMAL = 3,           /* rtNormal_           RGBA16F */
+    GK_PLANE_OBJECT_ID0 = 4,       /* rtObject0           R32_UINT 4 B/px */
+    GK_PLANE_OBJECT_ID1 = 5,       /* rtObject1           R32_UINT (previous frame) */
+    GK_PLANE_MOTION = 6,           /* rtMotionVector_     RG32F    8 B/px */
+    GK_PLANE_DEPTH = 7,            /* rtPrevDepth         R32F */
+    GK_PLANE_ACCUM_DIFFUSE = 8,    /* rtAccumlatedDiffuse RGBA16F */
+    GK_PLANE_ACCUM_SPECULAR = 9,   /* rtAccumlatedSpecular */
+    GK_PLANE_ACCUM_ALBEDO = 10,    /* rtAccumlatedAlbedo_ */
+    GK_PLANE_HISTORY_DIFFUSE = 11, /* rtPingPong0 */
+    GK_PLANE_HISTORY_SPECULAR = 12,/* rtPingPong1 */
+    GK_PLANE_HISTORY_ALBEDO = 13,  /* rtPingPong3 */
+    GK_PLANE_DENOISED = 14,        /* rtDenoised          RGBA16F (tonemapped final image) */
+    /* un-quantised integrator outputs kept for parity checks */
+    GK_PLANE_RADIANCE_DIFFUSE_F32 = 15, /* 4 x f32 */
+    GK_PLANE_RADIANCE_SPECULAR_F32 = 16,/* 4 x f32 */
+    GK_PLANE_PRIMARY_IDS = 17,     /* 2 x u32: {triangle, node-proxy index}, 0xffffffff = miss */
+    GK_PLANE_PRIMARY_T = 18,       /* f32 hit distance of the primary ray */
+    GK_PLANE_RAY_COUNT = 19,       /* u32 rays traced for the pixel this frame */
+    GK_PLANE_COUNT = 20
+} GkPlane;
+
+typedef struct GkFrameStats {
+    uint64_t primaryRays;   /* camera rays traced */
+    uint64_t extensionRays; /* closest-hit bounce rays */
+    uint64_t shadowRays;    /* any-hit rays */
+    uint32_t waves;         /* extend/shade iterations of the wavefront loop */
+    uint32_t launches;      /* kernels of this library launched for the frame */
+    float msTotal;          /* whole gk_render_frame on the device */
+    float msBvh;            /* instance update + TLAS build/refit, if it ran this frame */
+    float msGenerate, msExtend, msShade, msShadow, msAccumulate; /* integrator */
+    float msReproject, msDenoise;
+    uint64_t nodeVisits, triTests; /* only when traversal statistics are enabled */
+} GkFrameStats;
+
+typedef struct GkBvhInfo {
+    uint32_t blasCount, instanceCount;
+    uint64_t triangleCount;       /* unique triangles over all BLAS */
+    uint64_t instancedTriangles;  /* sum over ray-visible instances */
+    uint32_t blasNodes2, blasNodes8, tlasNodes2, tlasNodes8;
+    uint64_t bytesGeometry, bytesBvh;
+    float msBlasBuild, msTlasBuild, msRefit;
+} GkBvhInfo;
+
+int gk_abi_version(void);
+const char* gk_last_error(void);
+
+/* Replaces LogicRendererBase::OnDeviceSet + CreateSwapChain(extent)
+ * (src/Rendering/VulkanBaseRenderer.hpp:245-246; PathTracingRenderer.cpp:66-77). */
+GkStatus gk_create(const GkConfig* cfg, GkContext** out);
+/* Replaces DeleteSwapChain + destructor (PathTracingRenderer.cpp:79-95). */
+void gk_destroy(GkContext* ctx);
+/* Swap-chain resize without dropping the scene. */
+GkStatus gk_resize(GkContext* ctx, uint32_t width, uint32_t height);
+
+/* Replaces Scene::RebuildMeshBuffer's device upload (src/Assets/Scene.cpp:101-270) and
+ * RayTraceBaseRenderer::CreateBottomLevelStructures (RayTraceBaseRenderer.cpp:298-362):
+ * converts vertices to the fp16 GPUVertex layout, de-indexes fp32 triangles and builds one
+ * BLAS per model on the GPU. */
+GkStatus gk_upload_scene(GkContext* ctx, const GkSceneDesc* scene);
+/* Replaces Scene::UpdateMaterial (Scene.cpp:335-350). */
+GkStatus gk_update_materials(GkContext* ctx, const GkMaterial* materials, uint32_t count);
+/* Replaces Scene::UpdateNodesGpuDriven's upload (Scene.cpp:464-511) plus
+ * RayTraceBaseRenderer::AfterUpdateScene + the per-frame TLAS rebuild
+ * (RayTraceBaseRenderer.cpp:176-228).  `refit` != 0 keeps the TLAS topology and only refits
+ * boxes (valid when the instance count is unchanged); 0 rebuilds it. */
+GkStatus gk_update_instances(GkContext* ctx, const GkNodeProxy* nodes, uint32_t count, int refit);
+/* Optional probe grid for the path terminator (Scene.cpp:258-259 buffers; AmbientCube.slang).
+ * NULL (the default) means un-baked probes, i.e. all zero. */
+GkStatus gk_set_probes(GkContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels, size_t count);
+
+/* Replaces UniformBuffer::SetValue for the frame (VulkanBaseRenderer.cpp:1370-1374). */
+GkStatus gk_set_ubo(GkContext* ctx, const GkUniformBufferObject* ubo);
+
+/* Replaces PathTracingRenderer::Render (PathTracingRenderer.cpp:97-231): rt pass, the three
+ * reproject passes, the compose (JBF) pass and the history copy, then ObjectId0 -> ObjectId1
+ * (VulkanBaseRenderer.cpp:1287-1303). */
+GkStatus gk_render_frame(GkContext* ctx);
+/* Individual stages, for the multi-GPU compositor (trace on every rank, exchange, filter)
+ * and for the filter-only benchmark. */
+GkStatus gk_trace_frame(GkContext* ctx);   /* Core.PathTracing only */
+GkStatus gk_filter_frame(GkContext* ctx);  /* ReProject x3 + DenoiseJBF + history/id copy */
+
+/* Replaces NextEngine::RayCastGPU -> FCPUAccelerationStructure::RayCastInCPU
+ * (src/Runtime/Engine.cpp:647-653; CPUAccelerationStructure.cpp:283-307), batched as in
+ * Task.RayCast.comp.slang.  origin_dir: 6 floats per ray. */
+GkStatus gk_raycast(GkContext* ctx, const float* origin_dir, uint32_t count, GkRayCastResult* out);
+/* Closest-hit queries on arbitrary rays: 8 floats per ray {O.xyz, tmin, D.xyz, tmax};
+ * out_tuv 3 floats, out_ids {triangle, node-proxy index} per ray.  Host pointers. */
+GkStatus gk_intersect(GkContext* ctx, const float* rays, uint32_t count, float* out_tuv, uint32_t* out_ids);
+/* Same on device-resident buffers (no copies); rays must stay valid until gk_synchronize. */
+GkStatus gk_intersect_device(GkContext* ctx, const void* d_rays, uint32_t count, void* d_out_tuv, void* d_out_ids, int anyHit);
+
+/* Plane access. gk_readback/gk_upload_plane copy the whole plane (bytes must match
+ * gk_plane_bytes).  gk_plane_device returns the device pointer so that frame-end collectives
+ * (NCCL) can run on the planes in place. */
+size_t gk_plane_bytes(const GkContext* ctx, GkPlane plane);
+GkStatus gk_readback(GkContext* ctx, GkPlane plane, void* dst, size_t bytes);
+GkStatus gk_upload_plane(GkContext* ctx, GkPlane plane, const void* src, size_t bytes);
+void* gk_plane_device(GkContext* ctx, GkPlane plane);
+
+GkStatus gk_synchronize(GkContext* ctx);
+GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out);
+GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out);
+/* Enables node-visit / triangle-test counters in the traversal kernels (slower). */
+GkStatus gk_set_traversal_stats(GkContext* ctx, int enabled);
+/* CUDA stream used by the context (cudaStream_t), for callers that order their own work. */
+void* gk_stream(GkContext* ctx);
+/* Dumps the extension-ray queue of wave `wave` of the last frame (8 floats per ray) into a
+ * host buffer of `capacity` rays; returns the number of rays written through *count.  Used to
+ * hand the CPU baseline the very rays the GPU traced. Requires gk_set_ray_capture(ctx, wave). */
+GkStatus gk_set_ray_capture(GkContext* ctx, int wave);
+GkStatus gk_get_captured_rays(GkContext* ctx, float* rays, uint32_t capacity, uint32_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GKNEXT_CUDA_H_ */
