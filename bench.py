@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the path-tracing hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload room|cornell|city|bricks]
+
+A "step" is one frame of the hot path on synthetic input: per-frame UBO -> wavefront path tracer
+(generate / extend / shade / shadow / accumulate) -> fused temporal reprojection -> joint bilateral
+denoise + tonemap.  Default workload = BASELINE.json configs[1]: procedural 1M-triangle room,
+1920x1080, 1 spp, 4 bounces, temporal 16, JBF size 5.
+
+Prints ONE JSON line (rank 0).  `value` = rays traced by all ranks / device time of the K timed
+frames (scene, BVH and frame state resident in HBM); `e2e` = the same through the reference-facing
+renderer interface with the UBO coming from host memory and the final RGBA16F image read back to
+pinned host memory every frame.  `cpu_baseline` = the reference's CPU ray query (real tinybvh,
+oracle/_ref) on the very rays the GPU traced, all host threads.  `--impl reference` makes that the
+timed arm.  Multi-GPU (torchrun): image rows are interleaved across ranks in 16-row tiles, scene
+and BVH replicated, one NCCL all-gather of the integrator planes at frame end, filters replicated.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene, scene args, width, height, settings)
+    "room": ("room", (1000000, 1234), 1920, 1080, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
+    "cornell": ("cornell", (), 640, 360, dict(NumberOfSamples=8, NumberOfBounces=4, TemporalFrames=16, Denoiser=0, TAA=0, ProgressiveRender=1)),
+    "bricks": ("bricks", (200000, 42), 1920, 1080, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
+    "city": ("city", (40, 100, 7, 46), 3840, 2160, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
+}
+WORKLOAD_NAMES = {
+    "room": "C2: procedural 1M-triangle room (1280 instances of 6 meshes), 1920x1080, 1 spp, 4 bounces, sun+sky, reproject + JBF",
+    "cornell": "C1: built-in Cornell box, 640x360, 8 spp, 4 bounces",
+    "bricks": "C3: 200k instanced bricks, per-frame TLAS refit, 1920x1080, 1 spp, 4 bounces",
+    "city": "C4: 10M-triangle instanced city, 3840x2160, 1 spp per step, 4 bounces",
+}
+TILE_ROWS = 16
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="room", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def measure_l2_bandwidth(torch):
+    """L2-resident read bandwidth (GB/s): repeated reduction over a 48 MB buffer (L2 is 126 MB)."""
+    x = torch.empty(12 * 1024 * 1024, dtype=torch.float32, device="cuda").uniform_()
+    for _ in range(5):
+        x.sum()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 0.0
+    for _ in range(5):
+        e0.record()
+        for _ in range(20):
+            x.sum()
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 20 * x.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    scene_name, scene_args, W, H, settings = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, scene_name, scene_args, W, H, settings)
+
+    import torch
+    import torch.distributed as dist
+    import gknextrenderer_b200 as gk
+    from gknextrenderer_b200 import compositor as comp
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+
+    # ---- the reference-facing path: Assets::Scene -> LogicRendererBase-shaped renderer -> C ABI
+    eng = gk.Engine(scene_name, *scene_args)
+    eng.set(**settings)
+    host = gk.host_lib()
+    hr = host.gkh_renderer_create(eng.h, local_rank)
+    assert host.gkh_renderer_set_tile(hr, rank, world, TILE_ROWS) == 0
+
+    def chk(rc):
+        if rc != 0:
+            raise RuntimeError(host.gkh_last_error().decode())
+
+    chk(host.gkh_renderer_create_swapchain(hr, W, H))
+    chk(host.gkh_renderer_post_load_scene(hr))
+    ctx = C.c_void_p(host.gkh_renderer_context(hr))
+    r = gk.Renderer.__new__(gk.Renderer)  # wrap the context the host renderer owns
+    r.lib, r.h, r.width, r.height = gk.cuda_lib(), ctx, W, H
+    info_before = None
+    stream = torch.cuda.ExternalStream(r.stream(), device=torch.device(f"cuda:{local_rank}"))
+    dynamic = scene_name == "bricks"
+
+    def frame(step_index, exchange=True):
+        if dynamic:
+            eng.step_scene(step_index)
+        chk(host.gkh_renderer_before_next_frame(hr))  # Scene::UpdateNodes -> instances -> TLAS
+        if world == 1:
+            chk(host.gkh_renderer_render(hr))  # UBO fill + gk_set_ubo + gk_render_frame
+            st = r.stats()
+            return st.primaryRays + st.extensionRays + st.shadowRays, st.launches, st
+        ubo = eng.ubo(W, H)
+        r.set_ubo(ubo)
+        r.trace_frame()
+        st = r.stats()
+        rays, launches = st.primaryRays + st.extensionRays + st.shadowRays, st.launches
+        if exchange:
+            comp.composite_frame(r, rank, world, TILE_ROWS)
+        r.filter_frame()
+        eng.advance_frame()
+        return rays, launches + 2, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    n_warm = max(3, args.warmup)
+    for i in range(n_warm):
+        frame(i)
+    info = r.bvh_info()
+
+    # ---- timed: device-resident inputs
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = dict(rays=0, launches=0, ext=0.0, shd=0.0, shade=0.0, gen=0.0, acc=0.0, rep=0.0, jbf=0.0, bvh=0.0, eray=0, sray=0, pray=0, waves=0)
+    e0.record(stream)
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        rays, launches, st = frame(n_warm + i)
+        agg["rays"] += rays; agg["launches"] += launches
+        agg["ext"] += st.msExtend; agg["shd"] += st.msShadow; agg["shade"] += st.msShade; agg["gen"] += st.msGenerate; agg["acc"] += st.msAccumulate
+        agg["rep"] += st.msReproject; agg["jbf"] += st.msDenoise; agg["bvh"] += st.msBvh if dynamic else 0.0
+        agg["eray"] += st.extensionRays; agg["sray"] += st.shadowRays; agg["pray"] += st.primaryRays; agg["waves"] += st.waves
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- timed: end to end through the renderer interface, host UBO in, final image out
+    final_host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory()
+    fin_ptr = C.c_void_p(final_host.data_ptr())
+    fin_bytes = r.plane_bytes("DENOISED")
+    for i in range(2):
+        frame(n_warm + args.steps + i)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    rays_e2e = 0
+    for i in range(args.steps):
+        rr, _, _ = frame(n_warm + args.steps + 2 + i)
+        rays_e2e += rr
+        r._check(r.lib.gk_readback(r.h, gk.PLANES["DENOISED"], fin_ptr, fin_bytes))
+    e3.record(stream)
+    barrier()
+    e2e_ms = e2.elapsed_time(e3)
+    h2d = 784 + (info.instanceCount * 208 if dynamic else 0)
+    d2h = fin_bytes
+
+    # ---- reduce over ranks: max time, summed rays
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([agg["rays"], rays_e2e, agg["launches"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        total_rays, total_rays_e2e, total_launches = float(c[0]), float(c[1]), int(c[2])
+    else:
+        total_rays, total_rays_e2e, total_launches = float(agg["rays"]), float(rays_e2e), int(agg["launches"])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (extend): L2-level node/triangle traffic
+    r.set_traversal_stats(True)
+    rays1, _, st1 = frame(10_000)
+    r.set_traversal_stats(False)
+    traced = st1.extensionRays + st1.shadowRays + st1.primaryRays
+    nodes_per_ray = st1.nodeVisits / max(traced, 1)
+    tris_per_ray = st1.triTests / max(traced, 1)
+    bytes_per_ray = 48.0 + 128.0 * nodes_per_ray + 48.0 * tris_per_ray  # ray 32 + hit 16, 128-B node lines, 48-B triangle records
+    ext_rays = agg["eray"] + agg["pray"]
+    ext_ms = agg["ext"]
+    l2_peak = measure_l2_bandwidth(torch)
+    achieved = ext_rays * bytes_per_ray / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    px = W * H
+    filt_ms = (agg["rep"] + agg["jbf"]) / args.steps
+    roofline = {"kernel": "k_extend (closest-hit traversal, 8-wide quantised BVH)", "bound": "l2", "achieved": round(achieved, 1), "peak": round(l2_peak, 1), "unit": "GB/s",
+                "frac": round(achieved / l2_peak, 4) if l2_peak else None, "traffic": None,
+                "model": {"bytes_per_ray": round(bytes_per_ray, 1), "node_visits_per_ray": round(nodes_per_ray, 2), "tri_tests_per_ray": round(tris_per_ray, 2),
+                          "rays_per_launch_avg": round(ext_rays / max(agg["waves"], 1), 0), "ms_per_step": round(ext_ms / args.steps, 4),
+                          "Grays_per_s_in_kernel": round(ext_rays / (ext_ms * 1e-3) / 1e9, 4) if ext_ms > 0 else None},
+                "peak_source": "measured in this run: torch.sum over an L2-resident 48 MB buffer"}
+    roofline_filters = {"kernel": "k_reproject + k_denoise_jbf", "bound": "hbm", "achieved": round((96 + 40) * px / (filt_ms * 1e-3) / 1e9, 1) if filt_ms > 0 else None,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": round((96 + 40) * px / (filt_ms * 1e-3) / 1e9 / hbm_peak, 4) if filt_ms > 0 else None,
+                        "bytes_per_pixel": {"reproject": 96, "denoise": 40}, "ms_per_step": round(filt_ms, 4),
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+
+    # ---- CPU baseline: the reference's tinybvh on the rays the GPU traced (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline(eng, r, frame, W, H)
+
+    value = total_rays / (dev_ms * 1e-3) / 1e6
+    line = {
+        "metric": "path-tracing throughput (rays traced per second, whole frame incl. reproject + denoise) and ms/frame at the named resolution",
+        "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+        "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.workload], "width": W, "height": H, "spp": settings["NumberOfSamples"], "bounces": settings["NumberOfBounces"],
+                   "triangles_instanced": int(info.instancedTriangles), "triangles_unique": int(info.triangleCount), "instances": int(info.instanceCount),
+                   "partition": f"{TILE_ROWS}-row tiles interleaved over {world} rank(s), scene+BVH replicated",
+                   "l2_policy": "per-frame working set (path state + queues + planes, >500 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
+        "rays_per_step": round(total_rays / args.steps, 0), "gpu_launches": total_launches,
+        "e2e": {"value": round(total_rays_e2e / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "api": "CudaPathTracingRenderer::BeforeNextFrame + Render (host mirror of LogicRendererBase) + gk_readback(rtDenoised) to pinned memory"},
+        "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "shade", "acc", "rep", "jbf", "bvh")},
+        "host_gap_ms_per_step": round((wall_ms - dev_ms) / args.steps, 4),
+        "bvh": {"blas_build_ms": round(info.msBlasBuild, 3), "tlas_build_ms": round(info.msTlasBuild, 3), "tlas_refit_ms": round(info.msRefit, 3),
+                "wide_nodes_blas": int(info.blasNodes8), "wide_nodes_tlas": int(info.tlasNodes8), "bytes": int(info.bytesBvh + info.bytesGeometry)},
+        "roofline": roofline, "roofline_filters": roofline_filters, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _captured_sample(eng, r, frame_fn):
+    """Primary wave + the third extend wave (incoherent bounce rays) of one frame."""
+    out = []
+    for wave in (0, 2):
+        r.set_ray_capture(wave)
+        frame_fn(20_000 + wave)
+        out.append(r.captured_rays(r.width * r.height).copy())
+    r.set_ray_capture(-1)
+    return out
+
+
+def _cpu_rate(eng, rays_list, repeats=3):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    nodes, n = eng.update_nodes()
+    use_ref = ol.have_ref()
+    scene = ol.OracleScene(eng.scene_desc(), nodes, n, use_ref=use_ref)
+    threads = os.cpu_count() or 1
+    res = []
+    for rays in rays_list:
+        best = None
+        for _ in range(repeats):
+            scene.intersect(rays, threads=threads)
+            best = scene.last_seconds if best is None else min(best, scene.last_seconds)
+        res.append((len(rays), best))
+    return use_ref, threads, res
+
+
+def cpu_baseline(eng, r, frame_fn, W, H):
+    rays_list = _captured_sample(eng, r, frame_fn)
+    use_ref, threads, res = _cpu_rate(eng, rays_list)
+    total = sum(n for n, _ in res)
+    secs = sum(s for _, s in res)
+    return {"value": round(total / secs / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": "reference" if use_ref else "port",
+            "sample": f"{res[0][0]} primary rays ({res[0][0] / res[0][1] / 1e6:.2f} Mrays/s) + {res[1][0]} third-wave bounce rays ({res[1][0] / max(res[1][1], 1e-9) / 1e6:.2f} Mrays/s) "
+                      "captured from the GPU frame, traversal only, best of 3, tinybvh BVH::Intersect over the TLAS" + ("" if use_ref else " (oracle port)")}
+
+
+def reference_arm(args, scene_name, scene_args, W, H, settings):
+    """The reference's CPU implementation of the path (tinybvh ray query, CPUAccelerationStructure.cpp)
+    timed on the host cores.  Rays are the camera rays plus cosine-distributed bounce rays derived
+    from them on the CPU (no GPU is used by this arm)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gknextrenderer_b200 as gk
+    import oracle_lib as ol
+    eng = gk.Engine(scene_name, *scene_args)
+    eng.set(**settings)
+    eng.set(TAA=0)
+    nodes, n = eng.update_nodes()
+    use_ref = ol.have_ref()
+    scene = ol.OracleScene(eng.scene_desc(), nodes, n, use_ref=use_ref)
+    threads = os.cpu_count() or 1
+    prim = ol.primary_rays(eng.ubo(W, H), W, H, tmax=2000.0)
+    stride = max(1, len(prim) // 400000)  # bounded sample: ~0.4M primary + ~0.4M bounce rays per step
+    prim = prim[::stride]
+    tuv, ids = scene.intersect(prim, threads=threads)
+    hit = ids[:, 1] != 0xFFFFFFFF
+    rng = np.random.default_rng(1)
+    P = prim[hit, 0:3] + prim[hit, 4:7] * tuv[hit, 0:1] * np.float32(0.999)
+    d = rng.normal(size=P.shape).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    bounce = np.zeros((len(P), 8), np.float32)
+    bounce[:, 0:3], bounce[:, 3], bounce[:, 4:7], bounce[:, 7] = P, 1e-3, d, 1000.0
+    rays = np.concatenate([prim, bounce])
+    for _ in range(max(1, min(args.warmup, 2))):
+        scene.intersect(rays, threads=threads)
+    secs = 0.0
+    for _ in range(args.steps):
+        scene.intersect(rays, threads=threads)
+        secs += scene.last_seconds
+    value = args.steps * len(rays) / secs / 1e6
+    line = {"impl": "reference", "metric": "path-tracing throughput (rays traced per second) of the reference CPU ray path", "value": round(value, 3), "unit": "Mrays/s",
+            "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[args.workload], "width": W, "height": H},
+            "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": threads, "kind": "reference" if use_ref else "port",
+                             "sample": f"{len(prim)} camera rays (every {stride}th pixel) + {len(bounce)} uniformly random bounce rays from their hit points per step; "
+                                       "tinybvh BVH::Intersect over the TLAS, traversal only"},
+            "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,107 @@
+"""Multi-GPU frame compositor: one process per GPU, scene and BVH replicated,
+the image partitioned by interleaved row tiles, ONE exchange step at frame end.
+
+The reference has no multi-GPU path; this is the only collective the hot path needs.  Tile
+mode: rank r traces the rows with (row // tile_rows) % world == r (GkConfig.tileIndex/Count),
+then every rank all-gathers the integrator's output planes so that each holds the full
+G-buffer and can run the spatial/temporal filters with their halos locally.  Because a pixel's
+random sequence depends only on (x, y, frame), the union of the tiles is bit-identical to the
+single-GPU frame.
+
+torch is used only as plumbing here: `torch.distributed` (NCCL over NVLink on the GPU box,
+gloo in the CPU tests) moving bytes between the planes the CUDA library owns.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# planes the path tracer writes and the filters read (name, bytes per pixel)
+EXCHANGE_PLANES = [
+    ("OUTPUT_DIFFUSE", 8), ("OUTPUT_SPECULAR", 8), ("ALBEDO", 8), ("NORMAL", 8), ("OBJECT_ID0", 4), ("MOTION", 8),
+]
+PARITY_PLANES = [("RADIANCE_DIFFUSE_F32", 16), ("RADIANCE_SPECULAR_F32", 16), ("PRIMARY_IDS", 8), ("PRIMARY_T", 4), ("RAY_COUNT", 4), ("DEPTH", 4)]
+
+
+def owned_rows(height: int, tile_rows: int, rank: int, world: int) -> np.ndarray:
+    rows = np.arange(height)
+    return rows[(rows // tile_rows) % world == rank]
+
+
+def row_blocks(height: int, tile_rows: int, rank: int, world: int):
+    """[(first_row, row_count)] of the contiguous row blocks rank owns, in image order."""
+    out = []
+    b = rank
+    while b * tile_rows < height:
+        r0 = b * tile_rows
+        out.append((r0, min(tile_rows, height - r0)))
+        b += world
+    return out
+
+
+def padded_blocks(height: int, tile_rows: int, world: int) -> int:
+    """Row blocks per rank after padding so every rank contributes the same byte count."""
+    total = (height + tile_rows - 1) // tile_rows
+    return (total + world - 1) // world
+
+
+def pack_owned(plane2d, height, tile_rows, rank, world):
+    """Gather this rank's row blocks of a (H, row_bytes) uint8 plane view into a dense
+    (padded_blocks*tile_rows, row_bytes) send buffer (torch tensor in, torch tensor out)."""
+    import torch
+    nb = padded_blocks(height, tile_rows, world)
+    send = torch.zeros((nb * tile_rows, plane2d.shape[1]), dtype=plane2d.dtype, device=plane2d.device)
+    for i, (r0, cnt) in enumerate(row_blocks(height, tile_rows, rank, world)):
+        send[i * tile_rows: i * tile_rows + cnt] = plane2d[r0: r0 + cnt]
+    return send
+
+
+def unpack_all(gathered, plane2d, height, tile_rows, world):
+    """Scatter the all-gathered (world, padded_blocks*tile_rows, row_bytes) buffer back into the
+    full plane."""
+    for rank in range(world):
+        for i, (r0, cnt) in enumerate(row_blocks(height, tile_rows, rank, world)):
+            plane2d[r0: r0 + cnt] = gathered[rank, i * tile_rows: i * tile_rows + cnt]
+
+
+def all_gather_plane(plane2d, height, tile_rows, rank, world, group=None):
+    """In-place: after the call every rank's `plane2d` holds all rows."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return
+    send = pack_owned(plane2d, height, tile_rows, rank, world)
+    recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:  # gloo (CPU tests)
+        dist.all_gather([recv[i] for i in range(world)], send, group=group)
+    unpack_all(recv, plane2d, height, tile_rows, world)
+
+
+def device_plane_tensor(renderer, name: str, bytes_per_pixel: int):
+    """Zero-copy torch view (H, W*bytes_per_pixel) uint8 of a plane owned by the CUDA library."""
+    import torch
+    ptr = renderer.plane_device_ptr(name)
+    nbytes = renderer.height * renderer.width * bytes_per_pixel
+
+    class _Wrap:
+        __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+    t = torch.as_tensor(_Wrap(), device=f"cuda:{torch.cuda.current_device()}")
+    return t.view(renderer.height, renderer.width * bytes_per_pixel)
+
+
+def composite_frame(renderer, rank: int, world: int, tile_rows: int, planes=None, group=None):
+    """Frame-end exchange for tile mode: all-gather the integrator planes over NCCL."""
+    import torch
+    if world == 1:
+        return 0
+    planes = EXCHANGE_PLANES if planes is None else planes
+    renderer.synchronize()
+    moved = 0
+    for name, bpp in planes:
+        t = device_plane_tensor(renderer, name, bpp)
+        all_gather_plane(t, renderer.height, tile_rows, rank, world, group)
+        moved += t.numel()
+    torch.cuda.synchronize()
+    return moved

@@ -48,7 +48,7 @@ inline float xsqrt(float a) { return sqrtf(a); }
 inline float xfma(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
 
-// exact vector helpers (source order == oracle/orc_math.h)
+// exact vector helpers (plain left-to-right fp32, one rounding per operation)
 GK_HD f3 xadd3(f3 a, f3 b) { return mk3(xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)); }
 GK_HD f3 xsub3(f3 a, f3 b) { return mk3(xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)); }
 GK_HD f3 xmul3(f3 a, f3 b) { return mk3(xmul(a.x, b.x), xmul(a.y, b.y), xmul(a.z, b.z)); }
@@ -76,7 +76,7 @@ GK_HD float safeRcp(float x) // tiny_bvh.h:329
     return kFar;
 }
 
-// column-major 4x4 times vec4, summed as (c0*x + c1*y) + (c2*z + c3*w)  (orc_math.h mul)
+// column-major 4x4 times vec4, summed as (c0*x + c1*y) + (c2*z + c3*w)
 struct f4 {
     float x, y, z, w;
 };

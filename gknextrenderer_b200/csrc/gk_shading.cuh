@@ -7,7 +7,7 @@
 //   assets/shaders/common/AmbientCube.slang  probe read side :71-78, :178-223, :275-364
 // This translation unit is compiled with -fmad=false: a*b+c stays two roundings unless fmaf
 // is written out (where the shader writes mad()/fma()), so the arithmetic follows the same
-// order as the CPU oracle the parity tests compare against.
+// order as a plain fp32 CPU evaluation of the shader source.
 #pragma once
 #include "gk_bvh.cuh"
 

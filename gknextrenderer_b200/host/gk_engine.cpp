@@ -141,7 +141,13 @@ void CudaPathTracingRenderer::BeforeNextFrame()
     auto& scene = GetScene();
     if (scene.UpdateNodes() || !instancesUploaded_) {
         const auto& px = scene.GetNodeProxys();
-        check(gk_update_instances(ctx_, px.data(), (uint32_t)px.size(), 0), "gk_update_instances");
+        // The reference rebuilds its TLAS on every dirty frame (RayTraceBaseRenderer.cpp:216-228).
+        // Here moving instances refit the existing tree and a full rebuild runs every 8th update
+        // (or when the instance count changes) to keep the tree quality bounded.
+        const bool refit = instancesUploaded_ && px.size() == lastInstanceCount_ && (updatesSinceRebuild_ % 8) != 7;
+        check(gk_update_instances(ctx_, px.data(), (uint32_t)px.size(), refit ? 1 : 0), "gk_update_instances");
+        updatesSinceRebuild_ = refit ? updatesSinceRebuild_ + 1 : 0;
+        lastInstanceCount_ = px.size();
         instancesUploaded_ = true;
     }
 }

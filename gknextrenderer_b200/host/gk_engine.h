@@ -114,6 +114,8 @@ private:
     int device_;
     uint32_t tileIndex_ = 0, tileCount_ = 1, tileRows_ = 16;
     bool instancesUploaded_ = false;
+    size_t lastInstanceCount_ = 0;
+    uint32_t updatesSinceRebuild_ = 0;
 };
 
 } // namespace gk

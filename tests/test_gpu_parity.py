@@ -1,0 +1,350 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Run with -m gpu on a B200.
+
+Bars (BASELINE.json north_star):
+  * primary-ray hit (triangle, instance) ids: bit-exact vs the reference's CPU BVH query;
+    id differences are classified and only exact-distance ties are tolerated (reported),
+  * hit distance / barycentrics: bit-exact (same fp32 operation order, no FMA contraction),
+  * per-pixel radiance at N spp: relative RMSE <= 1e-3 and |mean difference| <= 1e-3 of the mean
+    (the integrator uses the reference RNG sequence; only sin/cos/sqrt ulp differences remain),
+  * RGBA16F G-buffer planes: equal to the oracle's values rounded to half,
+  * filters: |diff| <= 2 half-ulps (exp/pow differ by ulps between libm and CUDA), same NaN pattern.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import gknextrenderer_b200 as gk
+import oracle_lib as ol
+from gknextrenderer_b200._native import GkUniformBufferObject
+
+pytestmark = pytest.mark.gpu
+
+RADIANCE_RELRMSE = 1e-3
+RADIANCE_MEAN_REL = 1e-3
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _setup(scene, W, H, args=(), **settings):
+    eng = gk.Engine(scene, *args)
+    eng.set(TAA=0, **settings)
+    r = gk.Renderer(W, H, device=0)
+    r.upload_scene(eng.scene_desc())
+    eng.update_nodes()             # first tick: prev transform is the (0,-100,0) placeholder (Model.cpp:1357)
+    nodes, n = eng.update_nodes()  # steady state: combinedPrevTS = identity for static nodes
+    r.update_instances(nodes, n)
+    orc = ol.OracleScene(eng.scene_desc(), nodes, n)
+    return eng, r, orc, (nodes, n)
+
+
+def _random_rays(rng, n, lo, hi, tmax=1000.0, tmin=1e-3):
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.zeros((n, 8), np.float32)
+    r[:, 0:3], r[:, 3], r[:, 4:7], r[:, 7] = o, tmin, d, tmax
+    return r
+
+
+def _compare_hits(r, orc, rays, label):
+    g_tuv, g_ids = r.intersect(rays)
+    o_tuv, o_ids = orc.intersect(rays, threads=os.cpu_count() or 1)
+    differ = (g_ids != o_ids).any(axis=1)
+    ties = differ & (_bits(g_tuv[:, 0]) == _bits(o_tuv[:, 0]))
+    hard = differ & ~ties
+    print(f"[{label}] rays={len(rays)} id mismatches={int(differ.sum())} exact-t ties={int(ties.sum())} other={int(hard.sum())}")
+    assert hard.sum() == 0, f"{label}: {int(hard.sum())} rays hit a different triangle at a different distance: first {np.nonzero(hard)[0][:5]}"
+    assert ties.sum() <= max(2, len(rays) // 100000), f"{label}: too many exact-distance ties ({int(ties.sum())})"
+    same = ~differ
+    assert np.array_equal(_bits(g_tuv[same]), _bits(o_tuv[same])), f"{label}: t/u/v not bit-identical"
+    return int(ties.sum())
+
+
+def test_primary_hit_ids_cornell_640x360_bit_exact(built):
+    W, H = 640, 360
+    eng, r, orc, _ = _setup("cornell", W, H)
+    rays = ol.primary_rays(eng.ubo(W, H), W, H)
+    ties = _compare_hits(r, orc, rays, "cornell primary 640x360")
+    assert ties == 0
+
+
+def test_golden_tinybvh_vectors_on_gpu(built):
+    """The committed outputs of the real tinybvh, reproduced by the CUDA traversal."""
+    for scene, args, fixture in (("cornell", (), "cornell_tinybvh.npz"), ("room", (20000, 99), "room20k_tinybvh.npz")):
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", fixture))
+        eng, r, orc, _ = _setup(scene, 64, 64, args)
+        o_tuv, o_ids = orc.intersect(g["rays"])
+        if not np.array_equal(o_ids, g["ids"]):
+            pytest.skip("scene differs from the fixture's (different host libm)")
+        tuv, ids = r.intersect(g["rays"])
+        differ = (ids != g["ids"]).any(axis=1)
+        hard = differ & (_bits(tuv[:, 0]) != _bits(g["tuv"][:, 0]))
+        assert hard.sum() == 0 and differ.sum() <= 1
+        assert np.array_equal(_bits(tuv[~differ]), _bits(g["tuv"][~differ]))
+
+
+def test_incoherent_rays_and_tmin(built):
+    rng = np.random.default_rng(11)
+    eng, r, orc, _ = _setup("cornell", 64, 64)
+    _compare_hits(r, orc, _random_rays(rng, 200000, (-2.7, 0.05, -2.7), (2.7, 5.5, 2.7)), "cornell incoherent")
+    eng, r, orc, _ = _setup("room", 64, 64, (60000, 5))
+    _compare_hits(r, orc, _random_rays(rng, 300000, (-9.5, 0.1, -9.5), (9.5, 3.9, 9.5)), "room60k incoherent")
+    # degenerate inputs: zero-length direction, tmax below tmin, rays starting on geometry
+    weird = np.array([[0, 1, 0, 0, 0, 0, 0, 1000], [0, 1, 0, 5, 0, -1, 0, 2], [0, 0, 0, 0, 0, 1, 0, 1000], [0, 0, 0, 1e-3, 0, -1, 0, 1000]], np.float32)
+    g_tuv, g_ids = r.intersect(weird)
+    o_tuv, o_ids = orc.intersect(weird)
+    assert np.array_equal(g_ids, o_ids) and np.array_equal(_bits(g_tuv), _bits(o_tuv))
+
+
+def test_raycast_matches_raycastincpu(built):
+    W, H = 640, 360
+    eng, r, orc, _ = _setup("cornell", W, H)
+    eng.ubo(W, H)
+    od = []
+    for (x, y) in [(320, 180), (200, 100), (420, 300), (5, 5), (330, 20), (400, 250)]:
+        o, d = eng.screen_ray(x, y, W, H)
+        od.append(np.concatenate([o, d]))
+    od = np.array(od, np.float32)
+    a, b = r.raycast(od), orc.raycast(od)
+    for i in range(len(od)):
+        assert a[i].Hitted == b[i].Hitted and a[i].InstanceId == b[i].InstanceId
+        assert np.array_equal(_bits(np.float32(a[i].HitPoint[:] + a[i].Normal[:] + [a[i].T])), _bits(np.float32(b[i].HitPoint[:] + b[i].Normal[:] + [b[i].T])))
+
+
+def _radiance_check(r, o, label, W, H):
+    out = {}
+    for plane, key in (("RADIANCE_DIFFUSE_F32", "diffuse"), ("RADIANCE_SPECULAR_F32", "spec")):
+        g, ref = r.readback(plane)[..., :3].astype(np.float64), o[key][..., :3].astype(np.float64)
+        rel = np.sqrt(np.mean((g - ref) ** 2)) / (np.sqrt(np.mean(ref ** 2)) + 1e-30)
+        dmean = abs(g.mean() - ref.mean()) / (abs(ref.mean()) + 1e-30)
+        exact = int((g == ref).all(axis=2).sum())
+        print(f"[{label}] {key}: relRMSE={rel:.3e} mean-diff={dmean:.3e} bit-identical pixels={exact}/{W * H}")
+        assert rel <= RADIANCE_RELRMSE and dmean <= RADIANCE_MEAN_REL, (label, key, rel, dmean)
+        out[key] = (rel, dmean, exact)
+    return out
+
+
+def _gbuffer_check(r, o, label):
+    ids = r.readback("PRIMARY_IDS")
+    assert np.array_equal(ids, o["primIds"]), f"{label}: primary ids"
+    assert np.array_equal(r.readback("OBJECT_ID0"), o["objectId"])
+    for plane, key in (("ALBEDO", "albedo"), ("NORMAL", "normal")):
+        g = r.readback(plane)
+        assert np.array_equal(g.view(np.uint16), o[key].astype(np.float16).view(np.uint16)), f"{label}: {plane}"
+    assert np.array_equal(_bits(r.readback("MOTION")), _bits(o["motion"])), f"{label}: motion"
+    assert np.array_equal(_bits(r.readback("DEPTH")), _bits(o["depth"])), f"{label}: depth"
+    assert np.array_equal(r.readback("RAY_COUNT"), o["rayCount"]), f"{label}: rays per pixel"
+    for plane, key in (("OUTPUT_DIFFUSE", "diffuse"), ("OUTPUT_SPECULAR", "spec")):
+        g16 = r.readback(plane).astype(np.float32)
+        ref16 = o[key].astype(np.float16).astype(np.float32)
+        assert np.allclose(g16, ref16, rtol=2e-3, atol=1e-3), f"{label}: {plane}"
+
+
+def test_config1_cornell_640x360_8spp_4bounces(built):
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case."""
+    W, H = 640, 360
+    eng, r, orc, _ = _setup("cornell", W, H, NumberOfSamples=8, NumberOfBounces=4)
+    ubo = eng.ubo(W, H)
+    r.set_ubo(ubo)
+    r.trace_frame()
+    o = orc.render(ubo, W, H, threads=os.cpu_count() or 1)
+    _gbuffer_check(r, o, "cornell 640x360")
+    _radiance_check(r, o, "cornell 640x360 8spp", W, H)
+    st = r.stats()
+    assert st.primaryRays == W * H and st.primaryRays + st.extensionRays + st.shadowRays == int(o["rayCount"].sum())
+
+
+@pytest.mark.parametrize("frame", [0, 3])
+def test_sun_sky_materials_room(built, frame):
+    """Sun NEE, sky misses, metal / mixture / dielectric / emissive materials, rotated and
+    non-uniformly scaled instances (the Cornell box exercises none of these)."""
+    W, H = 320, 180
+    eng, r, orc, _ = _setup("room", W, H, (60000, 5), NumberOfSamples=2, NumberOfBounces=4, TotalFrames=frame)
+    ubo = eng.ubo(W, H)
+    assert ubo.HasSun == 1 and ubo.HasSky == 1
+    r.set_ubo(ubo)
+    r.trace_frame()
+    o = orc.render(ubo, W, H, threads=os.cpu_count() or 1)
+    _gbuffer_check(r, o, f"room60k f{frame}")
+    _radiance_check(r, o, f"room60k 2spp f{frame}", W, H)
+    assert r.stats().shadowRays > 0
+
+
+def test_depth_of_field_path(built):
+    W, H = 160, 90
+    eng, r, orc, _ = _setup("cornell", W, H, NumberOfSamples=1, NumberOfBounces=2, Aperture=0.3, FocalDistance=9.0)
+    ubo = eng.ubo(W, H)
+    r.set_ubo(ubo)
+    r.trace_frame()
+    o = orc.render(ubo, W, H, threads=os.cpu_count() or 1)
+    assert np.array_equal(r.readback("OBJECT_ID0"), o["objectId"])
+    g, ref = r.readback("RADIANCE_DIFFUSE_F32"), o["diffuse"]
+    assert (ref[..., 3] > 0).any(), "the test must actually defocus some pixels"
+    assert np.allclose(g[..., 3], ref[..., 3], rtol=1e-5, atol=1e-6)
+    rel = np.sqrt(np.mean((g[..., :3] - ref[..., :3]) ** 2)) / np.sqrt(np.mean(ref[..., :3] ** 2))
+    assert rel <= RADIANCE_RELRMSE
+
+
+def test_frame_is_deterministic_and_tiles_compose_bit_exactly(built):
+    W, H = 320, 180
+    eng = gk.Engine("room", 60000, 5)
+    eng.set(TAA=0, NumberOfSamples=1, NumberOfBounces=4)
+    ubo = eng.ubo(W, H)
+    nodes, n = eng.update_nodes()
+    full = gk.Renderer(W, H, device=0)
+    full.upload_scene(eng.scene_desc()); full.update_instances(nodes, n); full.set_ubo(ubo)
+    full.trace_frame()
+    a = {p: full.readback(p).copy() for p in ("RADIANCE_DIFFUSE_F32", "RADIANCE_SPECULAR_F32", "PRIMARY_IDS", "OUTPUT_DIFFUSE", "NORMAL", "MOTION")}
+    full.trace_frame()
+    for p in a:
+        assert np.array_equal(a[p].view(np.uint8), full.readback(p).view(np.uint8)), f"{p} not deterministic"
+    from gknextrenderer_b200 import compositor as comp
+    world, tr = 3, 16
+    union = {p: np.zeros_like(a[p]) for p in a}
+    for rank in range(world):
+        t = gk.Renderer(W, H, device=0, tile_index=rank, tile_count=world, tile_rows=tr)
+        t.upload_scene(eng.scene_desc()); t.update_instances(nodes, n); t.set_ubo(ubo)
+        t.trace_frame()
+        rows = comp.owned_rows(H, tr, rank, world)
+        for p in a:
+            union[p][rows] = t.readback(p)[rows]
+        assert t.stats().primaryRays == len(rows) * W
+        t.close()
+    for p in a:
+        assert np.array_equal(a[p].view(np.uint8), union[p].view(np.uint8)), f"tile union differs on {p}"
+
+
+def test_refit_equals_rebuild_after_moving_instances(built):
+    eng, r, orc, (nodes, n) = _setup("bricks", 64, 64, (3000, 42))
+    rng = np.random.default_rng(5)
+    rays = _random_rays(rng, 100000, (-20, 0.0, -20), (20, 3.0, 20))
+    rays[:, 5] = -np.abs(rays[:, 5]) - 0.2  # mostly downwards so that they hit bricks / ground
+    _compare_hits(r, orc, rays, "bricks rebuild f0")
+    for frame in (1, 2):
+        eng.step_scene(frame)
+        nodes, n = eng.update_nodes()
+        r.update_instances(nodes, n, refit=True)
+        orc.set_nodes(nodes, n)
+        _compare_hits(r, orc, rays, f"bricks refit f{frame}")
+    assert r.bvh_info().msRefit > 0
+
+
+# ---------------------------------------------------------------- filters
+def _filter_inputs(W, H, seed, frames=5):
+    rng = np.random.default_rng(seed)
+    f16 = np.float16
+    cell = 16
+    yy, xx = np.mgrid[0:H, 0:W]
+    ids = ((yy // cell) * ((W + cell - 1) // cell) + (xx // cell)).astype(np.uint32) % 61
+    ids[rng.uniform(size=(H, W)) < 0.03] = 65535
+    nrm_tab = rng.normal(size=(61, 3)); nrm_tab /= np.linalg.norm(nrm_tab, axis=1, keepdims=True)
+    normal = np.zeros((H, W, 4), np.float32)
+    normal[..., :3] = nrm_tab[ids % 61]
+    normal[..., :3] += rng.normal(scale=0.01, size=(H, W, 3))
+    normal[..., 3] = rng.uniform(0, 1, (H, W))
+    planes = {
+        "OUTPUT_DIFFUSE": np.exp(rng.normal(size=(H, W, 4))).astype(f16), "OUTPUT_SPECULAR": (0.3 * np.exp(rng.normal(size=(H, W, 4)))).astype(f16),
+        "ALBEDO": rng.uniform(0.05, 1.0, (H, W, 4)).astype(f16), "NORMAL": normal.astype(f16),
+        "HISTORY_DIFFUSE": np.exp(rng.normal(size=(H, W, 4))).astype(f16), "HISTORY_SPECULAR": (0.3 * np.exp(rng.normal(size=(H, W, 4)))).astype(f16),
+        "HISTORY_ALBEDO": rng.uniform(0.05, 1.0, (H, W, 4)).astype(f16),
+        "OBJECT_ID0": ids, "OBJECT_ID1": np.roll(ids, (1, 2), axis=(0, 1)).copy(),
+        "MOTION": rng.uniform(-2, 2, (H, W, 2)).astype(np.float32),
+    }
+    planes["MOTION"][rng.uniform(size=(H, W)) < 0.3] = 0.0
+    planes["OUTPUT_DIFFUSE"][rng.uniform(size=(H, W)) < 0.002] = f16(3000.0)  # fireflies (0/0 in the JBF)
+    u = GkUniformBufferObject()
+    u.ViewportRect[:] = [0, 0, W, H]
+    u.TemporalFrames, u.TotalFrames, u.BFSize = 16, frames, 5
+    u.BFSigma, u.BFSigmaLum, u.BFSigmaNormal, u.PaperWhiteNit = 2.0, 3.0, 0.005, 600.0
+    u.SelectedId = 7
+    return planes, u
+
+
+def _oracle_filters(planes, u, W, H):
+    lib = ol.load_oracle()
+    acc = {}
+    for ch, (src, hist, clamp, spatio) in {"DIFFUSE": ("OUTPUT_DIFFUSE", "HISTORY_DIFFUSE", 0, 1), "SPECULAR": ("OUTPUT_SPECULAR", "HISTORY_SPECULAR", 0, 1),
+                                           "ALBEDO": ("ALBEDO", "HISTORY_ALBEDO", 1, 0)}.items():
+        out = np.zeros((H, W, 4), np.uint16)
+        lib.orc_reproject(C.byref(u), W, H, clamp, spatio, ol.ptr(planes[src].view(np.uint16)), ol.ptr(planes[hist].view(np.uint16)), ol.ptr(planes["MOTION"]),
+                          ol.ptr(planes["OBJECT_ID0"]), ol.ptr(planes["OBJECT_ID1"]), ol.ptr(planes["NORMAL"].view(np.uint16)), ol.ptr(out))
+        acc[ch] = out
+    fin = np.zeros((H, W, 4), np.uint16)
+    lib.orc_denoise_jbf(C.byref(u), W, H, ol.ptr(acc["DIFFUSE"]), ol.ptr(acc["SPECULAR"]), ol.ptr(planes["NORMAL"].view(np.uint16)), ol.ptr(planes["OBJECT_ID0"]),
+                        ol.ptr(planes["OBJECT_ID1"]), ol.ptr(acc["ALBEDO"]), ol.ptr(fin))
+    return acc, fin
+
+
+def _half_close(g16, r16, label, ulps=2):
+    g, r = g16.view(np.float16).astype(np.float32), r16.view(np.float16).astype(np.float32)
+    assert np.array_equal(np.isnan(g), np.isnan(r)), f"{label}: NaN pattern differs"
+    ok = ~np.isnan(r)
+    gi, ri = g16.view(np.uint16).astype(np.int32)[ok], r16.view(np.uint16).astype(np.int32)[ok]
+    d = np.abs(gi - ri)
+    print(f"[{label}] half values differing: {int((d > 0).sum())}/{d.size}, max ulp distance {int(d.max())}")
+    assert d.max() <= ulps, f"{label}: max half-ulp distance {int(d.max())}"
+    return float((d > 0).mean())
+
+
+@pytest.mark.parametrize("W,H,variant", [(200, 120, "temporal"), (131, 77, "temporal"), (200, 120, "progressive"), (96, 64, "hdr_nofilter"), (96, 64, "nospatial")])
+def test_reproject_and_jbf_match_oracle(built, W, H, variant):
+    planes, u = _filter_inputs(W, H, seed=W * 7 + H)
+    if variant == "progressive":
+        u.ProgressiveRender, u.TemporalFrames = 1, 64
+    if variant == "hdr_nofilter":
+        u.HDR, u.BFSize = 1, 0
+    if variant == "nospatial":
+        u.DisableSpatialReuse, u.DebugDraw_Lighting = 1, 1
+    r = gk.Renderer(W, H, device=0)
+    for name, arr in planes.items():
+        r.upload_plane(name, arr)
+    r.set_ubo(u)
+    r.filter_frame()
+    acc, fin = _oracle_filters(planes, u, W, H)
+    exact_share = []
+    for ch in ("DIFFUSE", "SPECULAR", "ALBEDO"):
+        exact_share.append(_half_close(r.readback("ACCUM_" + ch), acc[ch], f"{variant} reproject {ch} {W}x{H}", ulps=1))
+    _half_close(r.readback("DENOISED"), fin, f"{variant} denoise {W}x{H}", ulps=2)
+    # after the frame the history planes hold the accumulated images and ObjectId1 the current ids
+    assert np.array_equal(r.readback("HISTORY_DIFFUSE").view(np.uint16), r.readback("ACCUM_DIFFUSE").view(np.uint16))
+    assert np.array_equal(r.readback("OBJECT_ID1"), planes["OBJECT_ID0"])
+
+
+def test_full_frame_pipeline_over_three_frames(built):
+    """Trace + reproject + denoise chained over frames with a moving camera, GPU vs oracle."""
+    W, H = 192, 108
+    eng, r, orc, _ = _setup("room", W, H, (60000, 5), NumberOfSamples=1, NumberOfBounces=3, Denoiser=1, TemporalFrames=8)
+    hist = {k: np.zeros((H, W, 4), np.uint16) for k in ("DIFFUSE", "SPECULAR", "ALBEDO")}
+    id1 = np.zeros((H, W), np.uint32)
+    lib = ol.load_oracle()
+    for frame in range(3):
+        eng.look_at((-9.0 + 0.05 * frame, 3.2, 9.0), (0.0, 1.2, 0.0))
+        ubo = eng.ubo(W, H)
+        r.set_ubo(ubo)
+        r.render_frame()
+        o = orc.render(ubo, W, H, threads=os.cpu_count() or 1)
+        src = {"DIFFUSE": o["diffuse"].astype(np.float16), "SPECULAR": o["spec"].astype(np.float16), "ALBEDO": o["albedo"].astype(np.float16)}
+        n16 = o["normal"].astype(np.float16)
+        acc = {}
+        for ch, clamp in (("DIFFUSE", 0), ("SPECULAR", 0), ("ALBEDO", 1)):
+            out = np.zeros((H, W, 4), np.uint16)
+            lib.orc_reproject(C.byref(ubo), W, H, clamp, 1 - clamp, ol.ptr(src[ch].view(np.uint16)), ol.ptr(hist[ch]), ol.ptr(o["motion"]), ol.ptr(o["objectId"]), ol.ptr(id1),
+                              ol.ptr(n16.view(np.uint16)), ol.ptr(out))
+            acc[ch] = out
+        fin = np.zeros((H, W, 4), np.uint16)
+        lib.orc_denoise_jbf(C.byref(ubo), W, H, ol.ptr(acc["DIFFUSE"]), ol.ptr(acc["SPECULAR"]), ol.ptr(n16.view(np.uint16)), ol.ptr(o["objectId"]), ol.ptr(id1), ol.ptr(acc["ALBEDO"]),
+                            ol.ptr(fin))
+        g = r.readback("DENOISED").astype(np.float32)
+        ref = fin.view(np.float16).astype(np.float32)
+        both = ~np.isnan(ref) & ~np.isnan(g)
+        assert (np.isnan(ref) != np.isnan(g)).mean() < 1e-3
+        rel = np.sqrt(np.mean((g[both] - ref[both]) ** 2)) / np.sqrt(np.mean(ref[both] ** 2))
+        print(f"[pipeline frame {frame}] final image relRMSE {rel:.3e}")
+        assert rel < 2e-3
+        hist, id1 = acc, o["objectId"].copy()
+        eng.advance_frame()
