@@ -342,11 +342,13 @@ void ProceduralRoom(Scene& scene, uint32_t targetTriangles, uint32_t seed)
 
     // room shell: floor + four walls, open to the sky (20 x 4 x 20 m)
     Model shell = Model::CreateBox(vec3(-10, -0.2f, -10), vec3(10, 0, 10));
-    Model wall = Model::CreateBox(vec3(-10, 0, -0.1f), vec3(10, 4, 0.1f));
-    shell.Append(wall, translate(vec3(0, 0, -10.1f)), 1);
-    shell.Append(wall, translate(vec3(0, 0, 10.1f)), 1);
-    shell.Append(wall, translate(vec3(-10.1f, 0, 0)) * mat4_cast(quat(vec3(0, 1.57079632679f, 0))), 1);
-    shell.Append(wall, translate(vec3(10.1f, 0, 0)) * mat4_cast(quat(vec3(0, 1.57079632679f, 0))), 1);
+    // no two faces of the shell are coplanar (coplanar overlaps are distance ties by construction)
+    Model wallZ = Model::CreateBox(vec3(-9.97f, -0.1f, -0.1f), vec3(9.97f, 4, 0.1f));
+    Model wallX = Model::CreateBox(vec3(-0.1f, -0.13f, -10.23f), vec3(0.1f, 4.05f, 10.23f));
+    shell.Append(wallZ, translate(vec3(0, 0, -10.1f)), 1);
+    shell.Append(wallZ, translate(vec3(0, 0, 10.1f)), 1);
+    shell.Append(wallX, translate(vec3(-10.1f, 0, 0)), 1);
+    shell.Append(wallX, translate(vec3(10.1f, 0, 0)), 1);
     scene.Models().push_back(shell);
     addNode(scene, "shell", vec3(0, 0, 0), quat(1, 0, 0, 0), vec3(1, 1, 1), 0, {0, 1});
 
