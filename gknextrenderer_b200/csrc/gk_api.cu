@@ -120,6 +120,7 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     c.tileIndex = cfg->tileIndex;
     c.tileRows = cfg->tileRows ? cfg->tileRows : 16;
     c.flags = cfg->flags;
+    if (const char* e = getenv("GK_COOP_THRESHOLD")) c.coopThreshold = (uint32_t)strtoul(e, nullptr, 10); // tuning / test hook
     if (c.tileIndex >= c.tileCount) {
         delete h;
         setLastError("gk_create: tileIndex >= tileCount");
@@ -145,7 +146,7 @@ void gk_destroy(GkContext* ctx)
     freeFrameResources(c);
     c.blasTree.release(), c.tlasTree.release();
     c.dModels.release(), c.dGpuVerts.release(), c.dIndices.release(), c.dMaterials.release(), c.dLights.release(), c.dFaceNormals.release();
-    c.dNodes.release(), c.dCubes.release(), c.dVoxels.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dInst.release();
+    c.dNodes.release(), c.dCubes.release(), c.dVoxels.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dBlasSrc.release(), c.dTlasSrc.release(), c.dInst.release();
     c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release();
     c.dCapture.release();
     for (cudaEvent_t e : c.evPool) cudaEventDestroy(e);

@@ -9,10 +9,23 @@
 //   instance transform ... tiny_bvh.h:2311-2315 (direction NOT re-normalised: t stays world-space)
 //   triangle test ........ tiny_bvh.h:6815-6843 (|a|<1e-7 reject, u,v in [0,1], u+v<=1, tmin<t<hit.t)
 // The tree itself is ours: an 8-wide node with child boxes quantised to 8 bits against the
-// node's own box (96 bytes used of a 128-byte line), built on the GPU (gk_bvh_build.cu).
+// node's own box, one 128-byte cache line per node, built on the GPU (gk_bvh_build.cu).
+//
+// Traversal is WARP-COOPERATIVE: eight lanes own one ray (four rays per warp).  B200 has no RT
+// cores and incoherent rays leave a one-ray-per-lane traversal at ~20 % SIMD efficiency
+// (profiles/), so the SIMD width is spent across the eight children of a node instead:
+//   node visit : lane j decodes and slab-tests child j, a ballot gives the hit mask, three
+//                shuffle-min steps pick the nearest child, the other hit lanes push themselves
+//                onto the ray's stack in shared memory in parallel (ballot + popc ranks)
+//   leaf visit : lane j runs the exact Möller–Trumbore test on triangle j (up to 8 per leaf),
+//                a shuffle-min picks the closest accepted hit
+// The per-ray state is replicated in the registers of the eight lanes, the stack lives in
+// shared memory (one row per ray).
 //
 // HBM/L2 layout
-//   WideNode  128 B stride, one cache line per node, read as 6 x 128-bit loads
+//   WideNode  128 B: 16-B header (origin, per-axis step exponents, child count) + 8 child
+//             records of 12 B {reference, qlo.xyz, qhi.xyz}: the 8 lanes read consecutive
+//             12-B records of one line
 //   TriRecord  48 B: v0 | e1 = v1-v0 | e2 = v2-v0 (the exact fp32 differences tinybvh
 //              forms per test), w lanes carry the original triangle index
 //   InstRecord 80 B: row-major inverse transform (64 B) + BLAS root reference + node index
@@ -26,14 +39,21 @@ namespace gk {
 //  TLAS leaf: bits[30:0] instance index
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kSentinel = 0xfffffffeu; // "return to the TLAS" stack marker
+constexpr uint32_t kBlasLeafMax = 8;        // triangles per BLAS leaf (one per lane)
+
+struct WideChild {
+    uint32_t ref;
+    uint8_t qlo[3];
+    uint8_t qhi[3];
+    uint8_t pad[2];
+};
+static_assert(sizeof(WideChild) == 12, "WideChild");
 
 struct __align__(16) WideNode {
-    float ox, oy, oz; // box origin (one quantisation step below the true minimum)
+    float ox, oy, oz;          // box origin (one quantisation step below the true minimum)
     uint8_t ex, ey, ez, count; // biased exponents of the per-axis step, valid children
-    uint32_t child[8];
-    uint8_t qlo[3][8];
-    uint8_t qhi[3][8];
-    uint32_t src[8]; // binary-tree node each slot was made from (refit re-quantises from these)
+    WideChild c[8];
+    uint32_t spare[4];
 };
 static_assert(sizeof(WideNode) == 128, "WideNode must fill one cache line");
 
@@ -75,8 +95,8 @@ struct TraversalStats {
 };
 
 // ---- exact triangle test -------------------------------------------------------------
-// Returns true and shortens `hit` when tmin < t < hit.t.  O, D are the (instance-space) ray.
-GK_HD bool triangleTest(const TriRecord& T, f3 O, f3 D, float tmin, Hit& hit, uint32_t instIdx)
+// Returns true when tmin < t < tmax; O, D are the (instance-space) ray.
+GK_HD bool triangleTest(const TriRecord& T, f3 O, f3 D, float tmin, float tmax, float& t, float& u, float& v)
 {
     const f3 e1 = mk3(T.e1x, T.e1y, T.e1z), e2 = mk3(T.e2x, T.e2y, T.e2z);
     const f3 h = xcross(D, e2);
@@ -84,73 +104,15 @@ GK_HD bool triangleTest(const TriRecord& T, f3 O, f3 D, float tmin, Hit& hit, ui
     if (fabsf(a) < 0.0000001f) return false;
     const float f = xdiv(1.0f, a);
     const f3 s = xsub3(O, mk3(T.v0x, T.v0y, T.v0z));
-    const float u = xmul(f, xdot(s, h));
+    u = xmul(f, xdot(s, h));
     if (u < 0 || u > 1) return false;
     const f3 q = xcross(s, e1);
-    const float v = xmul(f, xdot(D, q));
+    v = xmul(f, xdot(D, q));
     if (v < 0 || xadd(u, v) > 1) return false;
-    const float t = xmul(f, xdot(e2, q));
-    if (t > tmin && t < hit.t) {
-        hit.t = t, hit.u = u, hit.v = v, hit.prim = T.prim, hit.inst = instIdx;
-        return true;
-    }
-    return false;
+    t = xmul(f, xdot(e2, q));
+    return t > tmin && t < tmax;
 }
 
-// ---- wide-node box tests ---------------------------------------------------------------
-struct NodeTest {
-    float t[8]; // entry distance per slot, kFar when missed
-};
-
-GK_HD float byteToFloat(uint32_t word, int k)
-{
-#ifdef __CUDA_ARCH__
-    // 0x4B0000qq is 2^23 + q exactly; one PRMT + one FADD, both full-rate
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 + k)) - 8388608.0f;
-#else
-    return (float)((word >> (8 * k)) & 0xffu);
-#endif
-}
-
-GK_HD float expToFloat(uint32_t e8)
-{
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(e8 << 23);
-#else
-    uint32_t b = e8 << 23;
-    float f;
-    memcpy(&f, &b, 4);
-    return f;
-#endif
-}
-
-struct NodeWords { // one WideNode pulled into registers with 6 x 128-bit loads
-    uint4 q0, q1, q2, q3, q4, q5;
-};
-GK_HD NodeWords loadNode(const WideNode* n)
-{
-    NodeWords w;
-    const uint4* p = reinterpret_cast<const uint4*>(n);
-#ifdef __CUDA_ARCH__
-    w.q0 = __ldg(p + 0), w.q1 = __ldg(p + 1), w.q2 = __ldg(p + 2), w.q3 = __ldg(p + 3), w.q4 = __ldg(p + 4), w.q5 = __ldg(p + 5);
-#else
-    w.q0 = p[0], w.q1 = p[1], w.q2 = p[2], w.q3 = p[3], w.q4 = p[4], w.q5 = p[5];
-#endif
-    return w;
-}
-GK_HD uint32_t nodeChild(const NodeWords& w, int i)
-{
-    switch (i) {
-    case 0: return w.q1.x;
-    case 1: return w.q1.y;
-    case 2: return w.q1.z;
-    case 3: return w.q1.w;
-    case 4: return w.q2.x;
-    case 5: return w.q2.y;
-    case 6: return w.q2.z;
-    default: return w.q2.w;
-    }
-}
 GK_HD float asFloat(uint32_t u)
 {
 #ifdef __CUDA_ARCH__
@@ -162,126 +124,6 @@ GK_HD float asFloat(uint32_t u)
 #endif
 }
 
-// Slab test of all 8 quantised child boxes.  Conservative: boxes carry >= 1/64 step of
-// slack from the builder and the comparison allows 4 ulp on the exit distance.
-GK_HD uint32_t testWideNode(const NodeWords& N, f3 O, f3 rD, float tmin, float tmax, NodeTest& out)
-{
-    const uint32_t ec = N.q0.w;
-    const uint32_t count = ec >> 24;
-    const float sx = expToFloat(ec & 0xffu) * rD.x, sy = expToFloat((ec >> 8) & 0xffu) * rD.y, sz = expToFloat((ec >> 16) & 0xffu) * rD.z;
-    const float bx = (asFloat(N.q0.x) - O.x) * rD.x, by = (asFloat(N.q0.y) - O.y) * rD.y, bz = (asFloat(N.q0.z) - O.z) * rD.z;
-    // per axis pick which byte plane is the entry side
-    const bool nx = rD.x < 0, ny = rD.y < 0, nz = rD.z < 0;
-    const uint32_t loX[2] = {N.q3.x, N.q3.y}, loY[2] = {N.q3.z, N.q3.w}, loZ[2] = {N.q4.x, N.q4.y};
-    const uint32_t hiX[2] = {N.q4.z, N.q4.w}, hiY[2] = {N.q5.x, N.q5.y}, hiZ[2] = {N.q5.z, N.q5.w};
-    uint32_t mask = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const uint32_t nearX = nx ? hiX[half] : loX[half], farX = nx ? loX[half] : hiX[half];
-        const uint32_t nearY = ny ? hiY[half] : loY[half], farY = ny ? loY[half] : hiY[half];
-        const uint32_t nearZ = nz ? hiZ[half] : loZ[half], farZ = nz ? loZ[half] : hiZ[half];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float t0x = fmaf(byteToFloat(nearX, k), sx, bx), t1x = fmaf(byteToFloat(farX, k), sx, bx);
-            const float t0y = fmaf(byteToFloat(nearY, k), sy, by), t1y = fmaf(byteToFloat(farY, k), sy, by);
-            const float t0z = fmaf(byteToFloat(nearZ, k), sz, bz), t1z = fmaf(byteToFloat(farZ, k), sz, bz);
-            const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-            const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-            const int slot = half * 4 + k;
-            const bool hitBox = (tn <= tf * 1.0000005f) && (slot < (int)count);
-            out.t[slot] = hitBox ? tn : kFar;
-            mask |= hitBox ? (1u << slot) : 0u;
-        }
-    }
-    return mask;
-}
-
-// ---- two-level traversal ---------------------------------------------------------------
-constexpr int kStackSize = 48;
-
-struct StackEntry {
-    uint32_t ref;
-    float t;
-};
-
-// Closest hit (anyHit = false) or first hit (anyHit = true).  `hit.t` must hold tmax on entry.
-// Returns true if something was hit.  Dn is the NORMALISED world direction (tinybvh normalises
-// in the Ray constructor), O the world origin.
-template <bool kAnyHit, bool kStats>
-GK_HD bool traverseScene(const SceneView& S, f3 O, f3 Dn, float tmin, Hit& hit, TraversalStats* stats)
-{
-    StackEntry stack[kStackSize];
-    int sp = 0;
-    const float tmax0 = hit.t;
-    // current (TLAS = world, or instance) ray
-    f3 o = O, d = Dn;
-    f3 rd = mk3(safeRcp(Dn.x), safeRcp(Dn.y), safeRcp(Dn.z));
-    bool inBlas = false;
-    uint32_t curInst = 0;
-    uint32_t cur = S.tlasRoot;
-    if (S.instanceCount == 0) return false;
-
-    for (;;) {
-        if (!(cur & kLeafBit)) {
-            const NodeWords N = loadNode(inBlas ? S.blasNodes + cur : S.tlasNodes + cur);
-            if (kStats) stats->nodeVisits++;
-            NodeTest nt;
-            uint32_t mask = testWideNode(N, o, rd, tmin, hit.t, nt);
-            if (mask) {
-                // continue with the nearest child, push the rest with their entry distances
-                int best = -1;
-                float bt = kFar;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if ((mask >> i) & 1u) {
-                        if (nt.t[i] < bt || best < 0) bt = nt.t[i], best = i;
-                    }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (((mask >> i) & 1u) && i != best && sp < kStackSize) stack[sp].ref = nodeChild(N, i), stack[sp].t = nt.t[i], ++sp;
-                cur = nodeChild(N, best);
-                continue;
-            }
-        } else if (!inBlas) {
-            // TLAS leaf: enter the instance (tiny_bvh.h:2305-2315)
-            const uint32_t ii = cur & 0x7fffffffu;
-            const InstRecord& I = S.inst[ii];
-            if (sp < kStackSize) stack[sp].ref = kSentinel, stack[sp].t = 0.f, ++sp;
-            o = xformPoint(O, I.invT);
-            d = xformVector(Dn, I.invT);
-            rd = mk3(safeRcp(d.x), safeRcp(d.y), safeRcp(d.z));
-            inBlas = true;
-            curInst = I.node;
-            cur = I.blasRoot;
-            continue;
-        } else {
-            // BLAS leaf: 1..8 consecutive triangle records
-            const uint32_t first = (cur & 0x7fffffffu) >> 3, cnt = (cur & 7u) + 1u;
-            for (uint32_t k = 0; k < cnt; ++k) {
-                if (kStats) stats->triTests++;
-                const bool h = triangleTest(S.tris[first + k], o, d, tmin, hit, curInst);
-                if (kAnyHit && h) return true;
-            }
-        }
-        // pop
-        for (;;) {
-            if (sp == 0) return hit.t < tmax0;
-            --sp;
-            const uint32_t r = stack[sp].ref;
-            if (r == kSentinel) {
-                o = O, d = Dn;
-                rd = mk3(safeRcp(Dn.x), safeRcp(Dn.y), safeRcp(Dn.z));
-                inBlas = false;
-                continue;
-            }
-            if (stack[sp].t < hit.t) {
-                cur = r;
-                break;
-            }
-        }
-    }
-}
-
 // tinybvh's Ray constructor (tiny_bvh.h:562-567, :391-395)
 GK_HD f3 normalizeRayDir(f3 D)
 {
@@ -289,5 +131,259 @@ GK_HD f3 normalizeRayDir(f3 D)
     const float rl = (l == 0) ? 0.0f : xdiv(1.0f, l);
     return mk3(xmul(D.x, rl), xmul(D.y, rl), xmul(D.z, rl));
 }
+
+#ifdef __CUDACC__
+// ---- warp-cooperative traversal (device only) ------------------------------------------------
+constexpr int kStackSize = 48;
+constexpr int kStackStride = kStackSize + 1; // odd row stride: rows of different rays start in different banks
+constexpr int kRaysPerBlock = 32;            // 256 threads, 8 lanes per ray
+
+// Reciprocal direction for the BOX tests only (the triangle test never uses it, tiny_bvh.h:6815-6843):
+// one MUFU.RCP instead of the IEEE division sequence.  The 1-ulp error is covered by the slack of
+// the quantised boxes and the tolerance of the slab comparison.
+__device__ __forceinline__ float boxRcp(float x)
+{
+    if (fabsf(x) > 1e-12f) return __fdividef(1.0f, x);
+    return kFar;
+}
+__device__ __forceinline__ f3 boxRcp3(f3 d) { return mk3(boxRcp(d.x), boxRcp(d.y), boxRcp(d.z)); }
+
+__device__ __forceinline__ float byteToFloat(uint32_t word, int k)
+{
+    // 0x4B0000qq is 2^23 + q exactly; one PRMT + one FADD, both full-rate
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 + k)) - 8388608.0f;
+}
+
+// Closest hit (kAnyHit = false) or first hit (kAnyHit = true) for the ray owned by the calling
+// 8-lane group.  Every lane of the group passes the same ray and receives the same result.
+// `stackRow` points at the group's row of kStackSize uint2 entries in shared memory.
+// Dn is the NORMALISED world direction, hit.t must hold tmax on entry.
+template <bool kAnyHit, bool kStats>
+__device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, float tmin, Hit& hit, uint2* stackRow, TraversalStats* stats)
+{
+    const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, shift = lane & 24u;
+    const unsigned gmask = 0xffu << shift;
+    const float tmax0 = hit.t;
+    if (S.instanceCount == 0) return false;
+    f3 o = O, d = Dn;
+    const f3 rdWorld = boxRcp3(Dn);
+    f3 rd = rdWorld;
+    bool inBlas = false;
+    uint32_t curInst = 0;
+    uint32_t cur = S.tlasRoot;
+    int sp = 0;
+
+    for (;;) {
+        if (!(cur & kLeafBit)) {
+            // ---- node visit: lane `sub` tests child `sub`
+            const WideNode* N = (inBlas ? S.blasNodes : S.tlasNodes) + cur;
+            const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(N));
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(N) + 4 + 3 * sub;
+            const uint32_t ref = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2);
+            if (kStats && sub == 0) stats->nodeVisits++;
+            const uint32_t ec = hdr.w;
+            const float sx = __uint_as_float((ec & 0xffu) << 23) * rd.x, sy = __uint_as_float(((ec >> 8) & 0xffu) << 23) * rd.y,
+                        sz = __uint_as_float(((ec >> 16) & 0xffu) << 23) * rd.z;
+            const float bx = (__uint_as_float(hdr.x) - o.x) * rd.x, by = (__uint_as_float(hdr.y) - o.y) * rd.y, bz = (__uint_as_float(hdr.z) - o.z) * rd.z;
+            const float ax = fmaf(byteToFloat(w1, 0), sx, bx), cx = fmaf(byteToFloat(w1, 3), sx, bx);
+            const float ay = fmaf(byteToFloat(w1, 1), sy, by), cy = fmaf(byteToFloat(w2, 0), sy, by);
+            const float az = fmaf(byteToFloat(w1, 2), sz, bz), cz = fmaf(byteToFloat(w2, 1), sz, bz);
+            const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), tmin));
+            const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), hit.t));
+            // an empty slot is stored as lo = 255, hi = 0 on every axis and ref = kInvalid
+            const bool hitBox = (tn <= tf * 1.000001f) && (ref != kInvalid);
+            const unsigned m = (__ballot_sync(gmask, hitBox) >> shift) & 0xffu;
+            if (m) {
+                // nearest child: min over (entry distance | lane) keys; tn >= tmin >= 0 so the bits are monotone
+                const uint32_t key = __reduce_min_sync(gmask, hitBox ? ((__float_as_uint(tn) & ~7u) | sub) : 0xffffffffu);
+                const unsigned near = key & 7u;
+                const unsigned others = m & ~(1u << near);
+                const int room = kStackSize - sp;
+                if (hitBox && sub != near) {
+                    const int rank = __popc(others & ((1u << sub) - 1u));
+                    if (rank < room) stackRow[sp + rank] = make_uint2(ref, __float_as_uint(tn));
+                }
+                sp += min(__popc(others), room);
+                cur = __shfl_sync(gmask, ref, near + shift);
+                continue;
+            }
+        } else if (!inBlas) {
+            // ---- TLAS leaf: enter the instance (tiny_bvh.h:2305-2315); every lane transforms the ray
+            const uint32_t ii = cur & 0x7fffffffu;
+            const float4* ip = reinterpret_cast<const float4*>(S.inst + ii);
+            const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+            const uint4 tail = __ldg(reinterpret_cast<const uint4*>(ip + 4));
+            const float T[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+            if (sub == 0 && sp < kStackSize) stackRow[sp] = make_uint2(kSentinel, 0u);
+            sp = min(sp + 1, kStackSize);
+            o = xformPoint(O, T);
+            d = xformVector(Dn, T);
+            rd = boxRcp3(d);
+            inBlas = true;
+            curInst = tail.y;
+            cur = tail.x;
+            __syncwarp(gmask);
+            continue;
+        } else {
+            // ---- BLAS leaf: lane `sub` tests triangle `sub` of up to 8 consecutive records
+            const uint32_t first = (cur & 0x7fffffffu) >> 3, cnt = (cur & 7u) + 1u;
+            float t = 0.f, u = 0.f, v = 0.f;
+            uint32_t prim = 0;
+            bool ok = false;
+            if (sub < cnt) {
+                const float4* tp = reinterpret_cast<const float4*>(S.tris + first + sub);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                TriRecord T;
+                T.v0x = a.x, T.v0y = a.y, T.v0z = a.z, T.prim = __float_as_uint(a.w);
+                T.e1x = b.x, T.e1y = b.y, T.e1z = b.z, T.e2x = c.x, T.e2y = c.y, T.e2z = c.z;
+                ok = triangleTest(T, o, d, tmin, hit.t, t, u, v);
+                prim = T.prim;
+            }
+            if (kStats && sub == 0) stats->triTests += cnt;
+            const unsigned okm = (__ballot_sync(gmask, ok) >> shift) & 0xffu;
+            if (okm) {
+                if (kAnyHit) return true;
+                // closest accepted triangle; equal distances resolve to the first triangle of the leaf,
+                // which is what a sequential strict-less scan would keep
+                const uint32_t key = ok ? __float_as_uint(t) : 0x7f800000u;
+                const uint32_t kmin = __reduce_min_sync(gmask, key);
+                const unsigned win = (__ballot_sync(gmask, ok && key == kmin) >> shift) & 0xffu;
+                const int src = (__ffs(win) - 1) + shift;
+                hit.t = __shfl_sync(gmask, t, src);
+                hit.u = __shfl_sync(gmask, u, src);
+                hit.v = __shfl_sync(gmask, v, src);
+                hit.prim = __shfl_sync(gmask, prim, src);
+                hit.inst = curInst;
+            }
+        }
+        // ---- pop (the group barrier orders the pushes of the other lanes before these reads)
+        __syncwarp(gmask);
+        for (;;) {
+            if (sp == 0) return hit.t < tmax0;
+            --sp;
+            const uint2 e = stackRow[sp];
+            if (e.x == kSentinel) {
+                o = O, d = Dn, rd = rdWorld;
+                inBlas = false;
+                continue;
+            }
+            if (__uint_as_float(e.y) < hit.t) {
+                cur = e.x;
+                break;
+            }
+        }
+    }
+}
+
+// ---- one ray per lane ------------------------------------------------------------------------
+// Used for the large waves (coherent camera rays and the first bounces), where 32 rays per warp
+// amortise the node decode.  "while-while" form: every lane first descends through inner nodes
+// until it holds a leaf, then the warp processes leaves together.  The stack lives in local memory.
+struct LaneStack {
+    uint2 e[kStackSize];
+};
+
+template <bool kAnyHit, bool kStats>
+__device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, float tmin, Hit& hit, TraversalStats* stats)
+{
+    LaneStack stk;
+    int sp = 0;
+    const float tmax0 = hit.t;
+    if (S.instanceCount == 0) return false;
+    f3 o = O, d = Dn;
+    const f3 rdWorld = boxRcp3(Dn);
+    f3 rd = rdWorld;
+    bool inBlas = false;
+    uint32_t curInst = 0;
+    uint32_t cur = S.tlasRoot;
+
+    // pops the next live entry into `cur` (kInvalid when the stack is empty)
+#define GK_POP()                                                     \
+    for (;;) {                                                       \
+        if (sp == 0) { cur = kInvalid; break; }                      \
+        --sp;                                                        \
+        const uint2 e_ = stk.e[sp];                                  \
+        if (e_.x == kSentinel) { o = O, d = Dn, rd = rdWorld, inBlas = false; continue; } \
+        if (__uint_as_float(e_.y) < hit.t) { cur = e_.x; break; }    \
+    }
+
+    for (;;) {
+        // ---- (1) descend through inner nodes
+        while (!(cur & kLeafBit)) {
+            const uint4* np = reinterpret_cast<const uint4*>((inBlas ? S.blasNodes : S.tlasNodes) + cur);
+            const uint4 hdr = __ldg(np);
+            if (kStats) stats->nodeVisits++;
+            const uint32_t ec = hdr.w, count = ec >> 24;
+            const float sx = __uint_as_float((ec & 0xffu) << 23) * rd.x, sy = __uint_as_float(((ec >> 8) & 0xffu) << 23) * rd.y,
+                        sz = __uint_as_float(((ec >> 16) & 0xffu) << 23) * rd.z;
+            const float bx = (__uint_as_float(hdr.x) - o.x) * rd.x, by = (__uint_as_float(hdr.y) - o.y) * rd.y, bz = (__uint_as_float(hdr.z) - o.z) * rd.z;
+            float bestT = kFar;
+            uint32_t bestRef = kInvalid;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (half == 1 && count <= 4) break;
+                // 4 child records = 12 words = 3 x 128-bit loads
+                const uint4 q0 = __ldg(np + 1 + 3 * half), q1 = __ldg(np + 2 + 3 * half), q2 = __ldg(np + 3 + 3 * half);
+                const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t ref = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+                    const float ax = fmaf(byteToFloat(w1, 0), sx, bx), cx = fmaf(byteToFloat(w1, 3), sx, bx);
+                    const float ay = fmaf(byteToFloat(w1, 1), sy, by), cy = fmaf(byteToFloat(w2, 0), sy, by);
+                    const float az = fmaf(byteToFloat(w1, 2), sz, bz), cz = fmaf(byteToFloat(w2, 1), sz, bz);
+                    const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), tmin));
+                    const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), hit.t));
+                    if ((tn <= tf * 1.000001f) && (ref != kInvalid)) {
+                        // keep the nearest child in registers, push the other one
+                        uint32_t pr = ref;
+                        float pt = tn;
+                        if (tn < bestT) { pr = bestRef, pt = bestT, bestRef = ref, bestT = tn; }
+                        if (pr != kInvalid && sp < kStackSize) stk.e[sp++] = make_uint2(pr, __float_as_uint(pt));
+                    }
+                }
+            }
+            if (bestRef != kInvalid) cur = bestRef;
+            else { GK_POP() }
+        }
+        if (cur == kInvalid) break;
+        // ---- (2) leaves
+        if (!inBlas) {
+            const uint32_t ii = cur & 0x7fffffffu;
+            const float4* ip = reinterpret_cast<const float4*>(S.inst + ii);
+            const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
+            const uint4 tail = __ldg(reinterpret_cast<const uint4*>(ip + 4));
+            const float T[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+            if (sp < kStackSize) stk.e[sp++] = make_uint2(kSentinel, 0u);
+            o = xformPoint(O, T);
+            d = xformVector(Dn, T);
+            rd = boxRcp3(d);
+            inBlas = true;
+            curInst = tail.y;
+            cur = tail.x;
+            continue;
+        }
+        {
+            const uint32_t first = (cur & 0x7fffffffu) >> 3, cnt = (cur & 7u) + 1u;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const float4* tp = reinterpret_cast<const float4*>(S.tris + first + k);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                TriRecord T;
+                T.v0x = a.x, T.v0y = a.y, T.v0z = a.z, T.prim = __float_as_uint(a.w);
+                T.e1x = b.x, T.e1y = b.y, T.e1z = b.z, T.e2x = c.x, T.e2y = c.y, T.e2z = c.z;
+                float t, u, v;
+                if (kStats) stats->triTests++;
+                if (triangleTest(T, o, d, tmin, hit.t, t, u, v)) {
+                    if (kAnyHit) return true;
+                    hit.t = t, hit.u = u, hit.v = v, hit.prim = T.prim, hit.inst = curInst;
+                }
+            }
+        }
+        GK_POP()
+        if (cur == kInvalid) break;
+    }
+#undef GK_POP
+    return hit.t < tmax0;
+}
+#endif // __CUDACC__
 
 } // namespace gk

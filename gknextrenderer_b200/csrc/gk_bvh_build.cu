@@ -270,8 +270,8 @@ __global__ void k_collapse_seed(Bvh2View B, const uint32_t* __restrict__ groupRo
 }
 
 __global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksIn, uint32_t taskCount, uint32_t* __restrict__ tasksOut,
-                                 uint32_t* __restrict__ counters /* [0]=outCount [1]=wideCount */, WideNode* __restrict__ nodes, uint32_t leafMax, int tlas,
-                                 uint32_t nodeCapacity)
+                                 uint32_t* __restrict__ counters /* [0]=outCount [1]=wideCount */, WideNode* __restrict__ nodes, uint32_t* __restrict__ nodeSrc,
+                                 uint32_t leafMax, int tlas, uint32_t nodeCapacity)
 {
     const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
     if (ti >= taskCount) return;
@@ -315,20 +315,23 @@ __global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksI
     n.ox = n.oy = n.oz = 0.f;
     n.ex = n.ey = n.ez = 127;
     n.count = (uint8_t)cnt;
+    n.spare[0] = n.spare[1] = n.spare[2] = n.spare[3] = 0;
     int k = 0;
     for (int i = 0; i < 8; ++i) {
+        uint32_t src = kInvalid;
+        n.c[i].ref = kInvalid;
         if (i < cnt) {
-            n.src[i] = slot[i];
-            if (leaf[i]) n.child[i] = refs[i];
+            src = slot[i];
+            if (leaf[i]) n.c[i].ref = refs[i];
             else {
-                n.child[i] = base + k;
+                n.c[i].ref = base + k;
                 tasksOut[2 * (tbase + k)] = refs[i], tasksOut[2 * (tbase + k) + 1] = base + k;
                 ++k;
             }
-        } else {
-            n.src[i] = kInvalid, n.child[i] = kInvalid;
         }
-        for (int a = 0; a < 3; ++a) n.qlo[a][i] = 255, n.qhi[a][i] = 0;
+        nodeSrc[(size_t)w * 8 + i] = src; // binary-tree node each slot was made from (refit re-quantises from these)
+        for (int a = 0; a < 3; ++a) n.c[i].qlo[a] = 255, n.c[i].qhi[a] = 0;
+        n.c[i].pad[0] = n.c[i].pad[1] = 0;
     }
     uint4* o = reinterpret_cast<uint4*>(nodes + w);
     const uint4* s = reinterpret_cast<const uint4*>(&n);
@@ -353,7 +356,7 @@ __device__ __forceinline__ int chooseExponent(float lo, float hi)
     return min(max(e, -120), 120);
 }
 
-__global__ void k_quantise(Bvh2View B, WideNode* __restrict__ nodes, uint32_t count)
+__global__ void k_quantise(Bvh2View B, WideNode* __restrict__ nodes, const uint32_t* __restrict__ nodeSrc, uint32_t count)
 {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= count) return;
@@ -367,7 +370,7 @@ __global__ void k_quantise(Bvh2View B, WideNode* __restrict__ nodes, uint32_t co
     float4 lo[8], hi[8];
     float4 nlo = make_float4(kFar, kFar, kFar, 0), nhi = make_float4(-kFar, -kFar, -kFar, 0);
     for (int i = 0; i < (int)n.count; ++i) {
-        const uint32_t r = n.src[i];
+        const uint32_t r = nodeSrc[(size_t)w * 8 + i];
         if (r & kLeafBit) lo[i] = B.llo[r & 0x7fffffffu], hi[i] = B.lhi[r & 0x7fffffffu];
         else lo[i] = B.ilo[r], hi[i] = B.ihi[r];
         if (lo[i].x <= hi[i].x) {
@@ -385,18 +388,19 @@ __global__ void k_quantise(Bvh2View B, WideNode* __restrict__ nodes, uint32_t co
         if (i < (int)n.count && lo[i].x <= hi[i].x) {
             const float l3[3] = {lo[i].x, lo[i].y, lo[i].z}, h3[3] = {hi[i].x, hi[i].y, hi[i].z};
             for (int a = 0; a < 3; ++a) {
+                // >= 1/64 step of slack on both sides: the traversal's decode error is far below it
                 const float ql = floorf((l3[a] - org[a]) / step[a] - 0.015625f), qh = ceilf((h3[a] - org[a]) / step[a] + 0.015625f);
-                n.qlo[a][i] = (uint8_t)fminf(fmaxf(ql, 0.f), 255.f);
-                n.qhi[a][i] = (uint8_t)fminf(fmaxf(qh, 0.f), 255.f);
+                n.c[i].qlo[a] = (uint8_t)fminf(fmaxf(ql, 0.f), 255.f);
+                n.c[i].qhi[a] = (uint8_t)fminf(fmaxf(qh, 0.f), 255.f);
             }
         } else {
-            for (int a = 0; a < 3; ++a) n.qlo[a][i] = 255, n.qhi[a][i] = 0;
+            for (int a = 0; a < 3; ++a) n.c[i].qlo[a] = 255, n.c[i].qhi[a] = 0;
         }
     }
     uint4* o = reinterpret_cast<uint4*>(nodes + w);
     const uint4* s = reinterpret_cast<const uint4*>(&n);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) o[i] = s[i]; // src[] unchanged
+    for (int i = 0; i < 8; ++i) o[i] = s[i];
 }
 
 // ------------------------------------------------------------------ instances
@@ -542,12 +546,14 @@ static Bvh2View viewOf(const Lbvh& T)
 }
 
 // Step 6+7.  rootRef (device, one per group) receives the wide root reference of each group.
-static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax, bool tlas, DevBuf<WideNode>& nodes, uint32_t& nodeCount, uint32_t* dRootRef)
+static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax, bool tlas, DevBuf<WideNode>& nodes, DevBuf<uint32_t>& nodeSrc, uint32_t& nodeCount,
+                         uint32_t* dRootRef)
 {
     const uint32_t n = T.n;
     cudaStream_t st = c.stream;
     const uint32_t capacity = n + groups + 8; // a wide node has >= 2 children: at most n-1 nodes
     GK_CUDA(nodes.reserve(capacity));
+    GK_CUDA(nodeSrc.reserve(8 * (size_t)capacity));
     GK_CUDA(c.dTaskA.reserve(2 * (size_t)capacity));
     GK_CUDA(c.dTaskB.reserve(2 * (size_t)capacity));
     GK_CUDA(c.dCounters.reserve(8));
@@ -566,7 +572,7 @@ static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax,
         const uint32_t tasks = h[0];
         if (tasks == 0) break;
         GK_CUDA(cudaMemsetAsync(c.dCounters.p, 0, sizeof(uint32_t), st));
-        k_collapse_level<<<gridFor(tasks, 128), 128, 0, st>>>(B, in, tasks, out, c.dCounters.p, nodes.p, leafMax, tlas ? 1 : 0, capacity);
+        k_collapse_level<<<gridFor(tasks, 128), 128, 0, st>>>(B, in, tasks, out, c.dCounters.p, nodes.p, nodeSrc.p, leafMax, tlas ? 1 : 0, capacity);
         std::swap(in, out);
     }
     GK_CUDA(cudaMemcpyAsync(h, c.dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -576,7 +582,7 @@ static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax,
         setLastError("wide-node pool overflow");
         return GK_ERR_OUT_OF_MEMORY;
     }
-    if (nodeCount) k_quantise<<<gridFor(nodeCount, 128), 128, 0, st>>>(B, nodes.p, nodeCount);
+    if (nodeCount) k_quantise<<<gridFor(nodeCount, 128), 128, 0, st>>>(B, nodes.p, nodeSrc.p, nodeCount);
     GK_CUDA(cudaGetLastError());
     return GK_OK;
 }
@@ -601,7 +607,7 @@ GkStatus buildBlasForest(Context& c)
     if (s != GK_OK) return s;
     DevBuf<uint32_t> rootRef;
     GK_CUDA(rootRef.reserve(groups));
-    s = collapse(c, T, groups, 4, false, c.dBlasNodes, c.blasNodeCount, rootRef.p);
+    s = collapse(c, T, groups, kBlasLeafMax, false, c.dBlasNodes, c.dBlasSrc, c.blasNodeCount, rootRef.p);
     if (s != GK_OK) return s;
     k_model_bounds_from_groups<<<gridFor(groups), 256, 0, st>>>(c.dModels.p, groups, c.dGroupLo.p, c.dGroupHi.p, rootRef.p);
     cudaEventRecord(e1, st);
@@ -647,13 +653,13 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
     if (!refit) {
         DevBuf<uint32_t> rootRef;
         GK_CUDA(rootRef.reserve(1));
-        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.tlasNodeCount, rootRef.p);
+        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.dTlasSrc, c.tlasNodeCount, rootRef.p);
         if (s != GK_OK) return s;
         GK_CUDA(cudaMemcpyAsync(&c.tlasRoot, rootRef.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaStreamSynchronize(st));
         rootRef.release();
     } else if (c.tlasNodeCount) {
-        k_quantise<<<gridFor(c.tlasNodeCount, 128), 128, 0, st>>>(viewOf(T), c.dTlasNodes.p, c.tlasNodeCount);
+        k_quantise<<<gridFor(c.tlasNodeCount, 128), 128, 0, st>>>(viewOf(T), c.dTlasNodes.p, c.dTlasSrc.p, c.tlasNodeCount);
     }
     cudaEventRecord(e1, st);
     GK_CUDA(cudaGetLastError());

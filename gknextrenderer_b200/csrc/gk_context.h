@@ -126,6 +126,7 @@ struct Context {
     Lbvh blasTree, tlasTree;
     DevBuf<TriRecord> dTris;
     DevBuf<WideNode> dBlasNodes, dTlasNodes;
+    DevBuf<uint32_t> dBlasSrc, dTlasSrc; // 8 binary-tree references per wide node (refit)
     uint32_t blasNodeCount = 0, tlasNodeCount = 0;
     DevBuf<InstRecord> dInst;
     uint32_t tlasRoot = 0;
@@ -146,6 +147,7 @@ struct Context {
     uint32_t* hCounts = nullptr; // pinned
     TraversalStats* dTravStats = nullptr;
     bool travStats = false;
+    uint32_t coopThreshold = 65536; // waves smaller than this use the 8-lanes-per-ray traversal
     GkFrameStats stats{};
     cudaEvent_t evA = nullptr, evB = nullptr;
     std::vector<cudaEvent_t> evPool;

@@ -110,42 +110,60 @@ __global__ void __launch_bounds__(256) k_generate(const GkUniformBufferObject* _
 }
 
 // -------------------------------------------------------------------------------- extend / shadow
-template <bool kStats>
+// Two mappings of rays to lanes (gk_bvh.cuh):
+//   kCoop = false : one ray per lane, 256 rays per block   (large waves)
+//   kCoop = true  : eight lanes per ray, 32 rays per block (small waves: 4-5x lower latency per ray,
+//                   which is what bounds the long tail of nearly empty waves)
+__device__ __forceinline__ uint2* stackRowOf(uint2* stack) { return stack + (threadIdx.x >> 3) * kStackStride; }
+
+template <bool kAnyHit, bool kCoop, bool kStats>
+__device__ __forceinline__ bool traceQueueRay(const SceneView& V, const float4 o, const float4 d, Hit& h, uint2* stack, TraversalStats* local)
+{
+    h.t = d.w, h.u = 0, h.v = 0, h.prim = kInvalid, h.inst = kInvalid;
+    if (!(d.w > 0.0f)) return false;
+    const f3 dn = normalizeRayDir(mk3(d.x, d.y, d.z));
+    if (kCoop) return traverseCoop<kAnyHit, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, stackRowOf(stack), local);
+    return traverseLane<kAnyHit, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, local);
+}
+
+template <bool kCoop, bool kStats>
 __global__ void __launch_bounds__(256) k_extend(SceneView V, RayQueue Q, uint32_t count, TraversalStats* stats)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint2 stack[kCoop ? kRaysPerBlock * kStackStride : 1];
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = kCoop ? (gt >> 3) : gt;
     if (i >= count) return;
-    const float4 o = Q.o_tmin[i], d = Q.d_tmax[i];
+    const float4 o = __ldg(Q.o_tmin + i), d = __ldg(Q.d_tmax + i);
     Hit h;
-    h.t = d.w, h.u = 0, h.v = 0, h.prim = kInvalid, h.inst = kInvalid;
     TraversalStats local{0, 0};
-    if (d.w > 0.0f) {
-        const f3 dn = normalizeRayDir(mk3(d.x, d.y, d.z));
-        traverseScene<false, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, &local);
-    }
-    Q.hit_tuvp[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-    Q.hit_inst[i] = h.inst;
-    if (kStats) {
-        atomicAdd(&stats->nodeVisits, local.nodeVisits);
-        atomicAdd(&stats->triTests, local.triTests);
+    traceQueueRay<false, kCoop, kStats>(V, o, d, h, stack, &local);
+    if (!kCoop || (threadIdx.x & 7u) == 0) {
+        Q.hit_tuvp[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+        Q.hit_inst[i] = h.inst;
+        if (kStats) {
+            atomicAdd(&stats->nodeVisits, local.nodeVisits);
+            atomicAdd(&stats->triTests, local.triTests);
+        }
     }
 }
 
-template <bool kStats>
+template <bool kCoop, bool kStats>
 __global__ void __launch_bounds__(256) k_shadow(SceneView V, RayQueue Q, uint32_t count, TraversalStats* stats)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint2 stack[kCoop ? kRaysPerBlock * kStackStride : 1];
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = kCoop ? (gt >> 3) : gt;
     if (i >= count) return;
-    const float4 o = Q.o_tmin[i], d = Q.d_tmax[i];
+    const float4 o = __ldg(Q.o_tmin + i), d = __ldg(Q.d_tmax + i);
     Hit h;
-    h.t = d.w, h.u = 0, h.v = 0, h.prim = kInvalid, h.inst = kInvalid;
     TraversalStats local{0, 0};
-    const f3 dn = normalizeRayDir(mk3(d.x, d.y, d.z));
-    const bool occluded = traverseScene<true, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, &local);
-    Q.hit_inst[i] = occluded ? 1u : 0u;
-    if (kStats) {
-        atomicAdd(&stats->nodeVisits, local.nodeVisits);
-        atomicAdd(&stats->triTests, local.triTests);
+    const bool occluded = traceQueueRay<true, kCoop, kStats>(V, o, d, h, stack, &local);
+    if (!kCoop || (threadIdx.x & 7u) == 0) {
+        Q.hit_inst[i] = occluded ? 1u : 0u;
+        if (kStats) {
+            atomicAdd(&stats->nodeVisits, local.nodeVisits);
+            atomicAdd(&stats->triTests, local.triTests);
+        }
     }
 }
 
@@ -568,18 +586,19 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams P, PathState S, 
 }
 
 // -------------------------------------------------------------------------------- utilities
-template <bool kAny, bool kStats>
+template <bool kAny, bool kCoop, bool kStats>
 __global__ void __launch_bounds__(256) k_intersect(SceneView V, const float4* __restrict__ rays, uint32_t n, float* __restrict__ tuv, uint32_t* __restrict__ ids,
                                                    TraversalStats* stats)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint2 stack[kCoop ? kRaysPerBlock * kStackStride : 1];
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = kCoop ? (gt >> 3) : gt;
     if (i >= n) return;
-    const float4 o = rays[2 * i], d = rays[2 * i + 1];
+    const float4 o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
     Hit h;
-    h.t = d.w, h.u = 0, h.v = 0, h.prim = kInvalid, h.inst = kInvalid;
     TraversalStats local{0, 0};
-    const f3 dn = normalizeRayDir(mk3(d.x, d.y, d.z));
-    const bool hit = traverseScene<kAny, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, &local);
+    const bool hit = traceQueueRay<kAny, kCoop, kStats>(V, o, d, h, stack, &local);
+    if (kCoop && (threadIdx.x & 7u) != 0) return;
     if (tuv) tuv[3 * i] = h.t, tuv[3 * i + 1] = h.u, tuv[3 * i + 2] = h.v;
     if (ids) {
         if (kAny) ids[2 * i] = hit ? 1u : 0u, ids[2 * i + 1] = hit ? 1u : 0u;
@@ -589,6 +608,25 @@ __global__ void __launch_bounds__(256) k_intersect(SceneView V, const float4* __
         atomicAdd(&stats->nodeVisits, local.nodeVisits);
         atomicAdd(&stats->triTests, local.triTests);
     }
+}
+
+// Launch helpers: pick the lane mapping by wave size.
+template <bool kShadow>
+static void launchTrace(Context& c, const SceneView& V, const RayQueue& Q, uint32_t count)
+{
+    const bool coop = count < c.coopThreshold;
+    const unsigned grid = (unsigned)((count + (coop ? kRaysPerBlock : 256) - 1) / (coop ? kRaysPerBlock : 256));
+    cudaStream_t st = c.stream;
+    TraversalStats* ts = c.travStats ? c.dTravStats : nullptr;
+#define GK_LAUNCH(K, COOP, STATS) K<COOP, STATS><<<grid, 256, 0, st>>>(V, Q, count, ts)
+    if (kShadow) {
+        if (coop) { if (ts) GK_LAUNCH(k_shadow, true, true); else GK_LAUNCH(k_shadow, true, false); }
+        else { if (ts) GK_LAUNCH(k_shadow, false, true); else GK_LAUNCH(k_shadow, false, false); }
+    } else {
+        if (coop) { if (ts) GK_LAUNCH(k_extend, true, true); else GK_LAUNCH(k_extend, true, false); }
+        else { if (ts) GK_LAUNCH(k_extend, false, true); else GK_LAUNCH(k_extend, false, false); }
+    }
+#undef GK_LAUNCH
 }
 
 // -------------------------------------------------------------------------------- host side
@@ -762,14 +800,12 @@ GkStatus traceFrame(Context& c)
                 GK_CUDA(cudaMemcpy2DAsync(c.dCapture.p + 1, 32, c.extendQ[cur].d_tmax, 16, 16, countE, cudaMemcpyDeviceToDevice, st));
                 c.capturedCount = countE;
             }
-            if (c.travStats) k_extend<true><<<gridFor(countE), 256, 0, st>>>(V, c.extendQ[cur], countE, c.dTravStats);
-            else k_extend<false><<<gridFor(countE), 256, 0, st>>>(V, c.extendQ[cur], countE, nullptr);
+            launchTrace<false>(c, V, c.extendQ[cur], countE);
             fs.launches++;
         }
         const size_t b = mark();
         if (countS) {
-            if (c.travStats) k_shadow<true><<<gridFor(countS), 256, 0, st>>>(V, c.shadowQ[cur], countS, c.dTravStats);
-            else k_shadow<false><<<gridFor(countS), 256, 0, st>>>(V, c.shadowQ[cur], countS, nullptr);
+            launchTrace<true>(c, V, c.shadowQ[cur], countS);
             fs.launches++;
         }
         const size_t d = mark();
@@ -823,13 +859,16 @@ GkStatus intersectDevice(Context& c, const float4* rays, uint32_t n, float* tuv,
     }
     if (n == 0) return GK_OK;
     const SceneView V = c.view();
-    if (c.travStats) {
-        if (anyHit) k_intersect<true, true><<<gridFor(n), 256, 0, c.stream>>>(V, rays, n, tuv, ids, c.dTravStats);
-        else k_intersect<false, true><<<gridFor(n), 256, 0, c.stream>>>(V, rays, n, tuv, ids, c.dTravStats);
-    } else {
-        if (anyHit) k_intersect<true, false><<<gridFor(n), 256, 0, c.stream>>>(V, rays, n, tuv, ids, nullptr);
-        else k_intersect<false, false><<<gridFor(n), 256, 0, c.stream>>>(V, rays, n, tuv, ids, nullptr);
-    }
+    const bool coop = n < c.coopThreshold;
+    const unsigned grid = (unsigned)((n + (coop ? kRaysPerBlock : 256) - 1) / (coop ? kRaysPerBlock : 256));
+    TraversalStats* ts = c.travStats ? c.dTravStats : nullptr;
+#define GK_LAUNCH(ANY, COOP, STATS) k_intersect<ANY, COOP, STATS><<<grid, 256, 0, c.stream>>>(V, rays, n, tuv, ids, ts)
+#define GK_PICK(ANY)                                                                          \
+    if (coop) { if (ts) GK_LAUNCH(ANY, true, true); else GK_LAUNCH(ANY, true, false); }       \
+    else { if (ts) GK_LAUNCH(ANY, false, true); else GK_LAUNCH(ANY, false, false); }
+    if (anyHit) { GK_PICK(true) } else { GK_PICK(false) }
+#undef GK_PICK
+#undef GK_LAUNCH
     GK_CUDA(cudaGetLastError());
     return GK_OK;
 }
