@@ -239,14 +239,17 @@ def main():
     else:
         total_rays, total_rays_e2e, total_launches = float(agg["rays"]), float(rays_e2e), int(agg["launches"])
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        r.h = None
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (extend): L2-level node/triangle traffic
     r.set_traversal_stats(True)
-    rays1, _, st1 = frame(10_000)
+    rays1, _, st1 = frame(10_000, exchange=False)  # rank-local: the other ranks have left, no collective here
     r.set_traversal_stats(False)
     traced = st1.extensionRays + st1.shadowRays + st1.primaryRays
     nodes_per_ray = st1.nodeVisits / max(traced, 1)
@@ -300,6 +303,7 @@ def main():
         "roofline": roofline, "roofline_filters": roofline_filters, "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line))
+    r.h = None  # the context belongs to the host renderer
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -218,6 +218,15 @@ class Renderer:
     def plane_device_ptr(self, name) -> int:
         return int(self.lib.gk_plane_device(self.h, PLANES[name]) or 0)
 
+    def exchange_bytes(self) -> int:
+        return int(self.lib.gk_exchange_bytes(self.h))
+
+    def exchange_pack(self, d_staging: int):
+        self._check(self.lib.gk_exchange_pack(self.h, C.c_void_p(d_staging)))
+
+    def exchange_unpack(self, d_all: int):
+        self._check(self.lib.gk_exchange_unpack(self.h, C.c_void_p(d_all)))
+
     def stream(self) -> int:
         return int(self.lib.gk_stream(self.h) or 0)
 

@@ -146,6 +146,9 @@ CUDA_API = {
     "gk_readback": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "gk_upload_plane": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "gk_plane_device": (_P, [_P, C.c_int]),
+    "gk_exchange_bytes": (C.c_size_t, [_P]),
+    "gk_exchange_pack": (C.c_int, [_P, _P]),
+    "gk_exchange_unpack": (C.c_int, [_P, _P]),
     "gk_synchronize": (C.c_int, [_P]),
     "gk_get_stats": (C.c_int, [_P, C.POINTER(GkFrameStats)]),
     "gk_get_bvh_info": (C.c_int, [_P, C.POINTER(GkBvhInfo)]),

@@ -91,17 +91,28 @@ def device_plane_tensor(renderer, name: str, bytes_per_pixel: int):
     return t.view(renderer.height, renderer.width * bytes_per_pixel)
 
 
+_staging = {}
+
+
 def composite_frame(renderer, rank: int, world: int, tile_rows: int, planes=None, group=None):
-    """Frame-end exchange for tile mode: all-gather the integrator planes over NCCL."""
+    """Frame-end exchange for tile mode.  The CUDA library packs the rows this rank owns of the six
+    integrator planes into one staging buffer (one kernel), NCCL all-gathers the staging buffers
+    over NVLink, and the library scatters every rank's rows into the full planes (one kernel).
+    All three steps are ordered on the library's stream."""
     import torch
+    import torch.distributed as dist
     if world == 1:
         return 0
-    planes = EXCHANGE_PLANES if planes is None else planes
-    renderer.synchronize()
-    moved = 0
-    for name, bpp in planes:
-        t = device_plane_tensor(renderer, name, bpp)
-        all_gather_plane(t, renderer.height, tile_rows, rank, world, group)
-        moved += t.numel()
-    torch.cuda.synchronize()
-    return moved
+    nbytes = renderer.exchange_bytes()
+    key = (renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h), nbytes, world)
+    if key not in _staging:
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        _staging.clear()
+        _staging[key] = (torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.empty(world * nbytes, dtype=torch.uint8, device=dev),
+                         torch.cuda.ExternalStream(renderer.stream(), device=dev))
+    send, recv, stream = _staging[key]
+    renderer.exchange_pack(send.data_ptr())
+    with torch.cuda.stream(stream):
+        dist.all_gather_into_tensor(recv, send, group=group)
+    renderer.exchange_unpack(recv.data_ptr())
+    return nbytes

@@ -360,6 +360,22 @@ void* gk_plane_device(GkContext* ctx, GkPlane plane)
     return ctx->c.planes.p[resolvePlane(ctx->c, plane)];
 }
 
+size_t gk_exchange_bytes(const GkContext* ctx) { return ctx ? exchangeBytesPerRank(ctx->c) : 0; }
+
+GkStatus gk_exchange_pack(GkContext* ctx, void* d_staging)
+{
+    GK_CHECK_CTX(ctx);
+    if (!d_staging) return GK_ERR_INVALID_ARGUMENT;
+    return exchangePack(c, d_staging);
+}
+
+GkStatus gk_exchange_unpack(GkContext* ctx, const void* d_all)
+{
+    GK_CHECK_CTX(ctx);
+    if (!d_all) return GK_ERR_INVALID_ARGUMENT;
+    return exchangeUnpack(c, d_all);
+}
+
 GkStatus gk_synchronize(GkContext* ctx)
 {
     GK_CHECK_CTX(ctx);

@@ -180,6 +180,10 @@ GkStatus raycastBatch(Context& c, const float* originDir, uint32_t n, GkRayCastR
 // gk_filters.cu
 GkStatus filterFrame(Context& c);
 void applyPendingHistorySwap(Context& c);
+// gk_exchange.cu
+size_t exchangeBytesPerRank(const Context& c);
+GkStatus exchangePack(Context& c, void* dStaging);
+GkStatus exchangeUnpack(Context& c, const void* dAll);
 
 } // namespace gk
 

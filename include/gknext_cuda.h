@@ -161,6 +161,16 @@ GkStatus gk_readback(GkContext* ctx, GkPlane plane, void* dst, size_t bytes);
 GkStatus gk_upload_plane(GkContext* ctx, GkPlane plane, const void* src, size_t bytes);
 void* gk_plane_device(GkContext* ctx, GkPlane plane);
 
+/* Frame-end exchange of the tile-partitioned frame (multi-GPU compositor).  gk_exchange_pack
+ * gathers the rows this context owns of the six integrator planes the filters read (diffuse,
+ * specular, albedo, normal, object id, motion: 44 B/pixel) into a device staging buffer of
+ * gk_exchange_bytes() bytes; after an all-gather of the staging buffers over NCCL,
+ * gk_exchange_unpack scatters tileCount x gk_exchange_bytes() bytes (rank-major) back into the
+ * full planes.  Device pointers; both calls enqueue on the context stream. */
+size_t gk_exchange_bytes(const GkContext* ctx);
+GkStatus gk_exchange_pack(GkContext* ctx, void* d_staging);
+GkStatus gk_exchange_unpack(GkContext* ctx, const void* d_all);
+
 GkStatus gk_synchronize(GkContext* ctx);
 GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out);
 GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out);
