@@ -11,21 +11,24 @@
 // The tree itself is ours: an 8-wide node with child boxes quantised to 8 bits against the
 // node's own box, one 128-byte cache line per node, built on the GPU (gk_bvh_build.cu).
 //
-// Traversal is WARP-COOPERATIVE: eight lanes own one ray (four rays per warp).  B200 has no RT
-// cores and incoherent rays leave a one-ray-per-lane traversal at ~20 % SIMD efficiency
-// (profiles/), so the SIMD width is spent across the eight children of a node instead:
-//   node visit : lane j decodes and slab-tests child j, a ballot gives the hit mask, three
-//                shuffle-min steps pick the nearest child, the other hit lanes push themselves
-//                onto the ray's stack in shared memory in parallel (ballot + popc ranks)
-//   leaf visit : lane j runs the exact Möller–Trumbore test on triangle j (up to 8 per leaf),
-//                a shuffle-min picks the closest accepted hit
-// The per-ray state is replicated in the registers of the eight lanes, the stack lives in
-// shared memory (one row per ray).
+// B200 has no RT cores; traversal is issue-bound shader code (profiles/), so the design goal is
+// fewest instructions per box test and highest lane utilisation:
+//   * box test = 6 PRMT + 6 FFMA + 2 three-input min/max + compare per child.  A child plane byte
+//     q is turned into the float 2^23+q by ONE byte-permute (the constant bytes 0x00,0x4B live in
+//     the child record itself), the -2^23 is folded into the FMA addend, and the permute selectors
+//     pick the entry / exit plane by the sign of the ray direction, so no per-axis min/max remains.
+//     The folded constant costs at most half a quantisation step of precision; the builder pads
+//     every box by one full step, so the test stays conservative.
+//   * two ray-to-lane mappings:
+//       one ray per lane (large waves): "while-while" traversal, every lane descends to a leaf,
+//         then the warp processes leaves together; stack in local memory;
+//       cooperative groups (small waves): eight lanes own one ray, lane j tests child j / triangle j,
+//         ballots and warp reductions pick the nearest; ~5x lower latency per ray, which bounds the
+//         long tail of nearly empty waves.
 //
 // HBM/L2 layout
 //   WideNode  128 B: 16-B header (origin, per-axis step exponents, child count) + 8 child
-//             records of 12 B {reference, qlo.xyz, qhi.xyz}: the 8 lanes read consecutive
-//             12-B records of one line
+//             records of 12 B {reference | qlo.xyz qhi.x | qhi.yz 0x00 0x4B}
 //   TriRecord  48 B: v0 | e1 = v1-v0 | e2 = v2-v0 (the exact fp32 differences tinybvh
 //              forms per test), w lanes carry the original triangle index
 //   InstRecord 80 B: row-major inverse transform (64 B) + BLAS root reference + node index
@@ -39,18 +42,18 @@ namespace gk {
 //  TLAS leaf: bits[30:0] instance index
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kSentinel = 0xfffffffeu; // "return to the TLAS" stack marker
-constexpr uint32_t kBlasLeafMax = 8;        // triangles per BLAS leaf (one per lane)
+constexpr uint32_t kBlasLeafMax = 8;        // triangles per BLAS leaf (one per lane in the cooperative mapping)
 
 struct WideChild {
     uint32_t ref;
     uint8_t qlo[3];
     uint8_t qhi[3];
-    uint8_t pad[2];
+    uint8_t k00, k4b; // constant bytes 0x00 and 0x4B: the upper bytes of the float 2^23 + q
 };
 static_assert(sizeof(WideChild) == 12, "WideChild");
 
 struct __align__(16) WideNode {
-    float ox, oy, oz;          // box origin (one quantisation step below the true minimum)
+    float ox, oy, oz;          // box origin (two quantisation steps below the true minimum)
     uint8_t ex, ey, ez, count; // biased exponents of the per-axis step, valid children
     WideChild c[8];
     uint32_t spare[4];
@@ -133,13 +136,13 @@ GK_HD f3 normalizeRayDir(f3 D)
 }
 
 #ifdef __CUDACC__
-// ---- warp-cooperative traversal (device only) ------------------------------------------------
 constexpr int kStackSize = 48;
 constexpr int kStackStride = kStackSize + 1; // odd row stride: rows of different rays start in different banks
-constexpr int kRaysPerBlock = 32;            // 256 threads, 8 lanes per ray
+constexpr int kRaysPerBlock = 32;            // cooperative mapping: 256 threads, 8 lanes per ray
+constexpr float kBoxTolerance = 1.000001f;   // slab comparison slack on the exit distance
 
 // Reciprocal direction for the BOX tests only (the triangle test never uses it, tiny_bvh.h:6815-6843):
-// one MUFU.RCP instead of the IEEE division sequence.  The 1-ulp error is covered by the slack of
+// one MUFU.RCP instead of the IEEE division sequence.  Its 1-ulp error is covered by the padding of
 // the quantised boxes and the tolerance of the slab comparison.
 __device__ __forceinline__ float boxRcp(float x)
 {
@@ -148,16 +151,49 @@ __device__ __forceinline__ float boxRcp(float x)
 }
 __device__ __forceinline__ f3 boxRcp3(f3 d) { return mk3(boxRcp(d.x), boxRcp(d.y), boxRcp(d.z)); }
 
-__device__ __forceinline__ float byteToFloat(uint32_t word, int k)
+// Byte-permute selectors for the six planes of a child record {w1 = qlo.x qlo.y qlo.z qhi.x,
+// w2 = qhi.y qhi.z 0x00 0x4B}: result bytes = [plane byte, 0x00, 0x00, 0x4B] = float(2^23 + q).
+struct PlaneSel {
+    uint32_t nx, fx, ny, fy, nz, fz; // entry ("near") and exit ("far") plane per axis
+};
+__device__ __forceinline__ PlaneSel makePlaneSel(f3 rd)
 {
-    // 0x4B0000qq is 2^23 + q exactly; one PRMT + one FADD, both full-rate
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 + k)) - 8388608.0f;
+    PlaneSel s;
+    const bool x = rd.x < 0, y = rd.y < 0, z = rd.z < 0;
+    s.nx = 0x7660u | (x ? 3u : 0u), s.fx = 0x7660u | (x ? 0u : 3u);
+    s.ny = 0x7660u | (y ? 4u : 1u), s.fy = 0x7660u | (y ? 1u : 4u);
+    s.nz = 0x7660u | (z ? 5u : 2u), s.fz = 0x7660u | (z ? 2u : 5u);
+    return s;
 }
 
-// Closest hit (kAnyHit = false) or first hit (kAnyHit = true) for the ray owned by the calling
-// 8-lane group.  Every lane of the group passes the same ray and receives the same result.
-// `stackRow` points at the group's row of kStackSize uint2 entries in shared memory.
-// Dn is the NORMALISED world direction, hit.t must hold tmax on entry.
+struct NodeFrame { // per node visit: t(q) = fma(2^23 + q, s, b)
+    float sx, sy, sz, bx, by, bz;
+};
+__device__ __forceinline__ NodeFrame makeNodeFrame(const uint4 hdr, f3 o, f3 rd)
+{
+    NodeFrame F;
+    const uint32_t ec = hdr.w;
+    F.sx = __uint_as_float((ec & 0xffu) << 23) * rd.x, F.sy = __uint_as_float(((ec >> 8) & 0xffu) << 23) * rd.y, F.sz = __uint_as_float(((ec >> 16) & 0xffu) << 23) * rd.z;
+    F.bx = fmaf(-8388608.0f, F.sx, (__uint_as_float(hdr.x) - o.x) * rd.x);
+    F.by = fmaf(-8388608.0f, F.sy, (__uint_as_float(hdr.y) - o.y) * rd.y);
+    F.bz = fmaf(-8388608.0f, F.sz, (__uint_as_float(hdr.z) - o.z) * rd.z);
+    return F;
+}
+// true when the ray enters the child box before leaving it; tn = entry distance
+__device__ __forceinline__ bool childTest(const NodeFrame& F, const PlaneSel& S, uint32_t w1, uint32_t w2, float tmin, float tmax, float& tn)
+{
+    const float t0x = fmaf(__uint_as_float(__byte_perm(w1, w2, S.nx)), F.sx, F.bx), t1x = fmaf(__uint_as_float(__byte_perm(w1, w2, S.fx)), F.sx, F.bx);
+    const float t0y = fmaf(__uint_as_float(__byte_perm(w1, w2, S.ny)), F.sy, F.by), t1y = fmaf(__uint_as_float(__byte_perm(w1, w2, S.fy)), F.sy, F.by);
+    const float t0z = fmaf(__uint_as_float(__byte_perm(w1, w2, S.nz)), F.sz, F.bz), t1z = fmaf(__uint_as_float(__byte_perm(w1, w2, S.fz)), F.sz, F.bz);
+    tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+    return tn <= tf * kBoxTolerance;
+}
+
+// ---- cooperative mapping: eight lanes per ray ---------------------------------------------------
+// Every lane of the group passes the same ray and receives the same result.  `stackRow` points at
+// the group's row of kStackSize uint2 entries in shared memory.  Dn is the NORMALISED world
+// direction, hit.t must hold tmax on entry.
 template <bool kAnyHit, bool kStats>
 __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, float tmin, Hit& hit, uint2* stackRow, TraversalStats* stats)
 {
@@ -167,7 +203,9 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
     if (S.instanceCount == 0) return false;
     f3 o = O, d = Dn;
     const f3 rdWorld = boxRcp3(Dn);
+    const PlaneSel selWorld = makePlaneSel(rdWorld);
     f3 rd = rdWorld;
+    PlaneSel sel = selWorld;
     bool inBlas = false;
     uint32_t curInst = 0;
     uint32_t cur = S.tlasRoot;
@@ -181,17 +219,9 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
             const uint32_t* cw = reinterpret_cast<const uint32_t*>(N) + 4 + 3 * sub;
             const uint32_t ref = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2);
             if (kStats && sub == 0) stats->nodeVisits++;
-            const uint32_t ec = hdr.w;
-            const float sx = __uint_as_float((ec & 0xffu) << 23) * rd.x, sy = __uint_as_float(((ec >> 8) & 0xffu) << 23) * rd.y,
-                        sz = __uint_as_float(((ec >> 16) & 0xffu) << 23) * rd.z;
-            const float bx = (__uint_as_float(hdr.x) - o.x) * rd.x, by = (__uint_as_float(hdr.y) - o.y) * rd.y, bz = (__uint_as_float(hdr.z) - o.z) * rd.z;
-            const float ax = fmaf(byteToFloat(w1, 0), sx, bx), cx = fmaf(byteToFloat(w1, 3), sx, bx);
-            const float ay = fmaf(byteToFloat(w1, 1), sy, by), cy = fmaf(byteToFloat(w2, 0), sy, by);
-            const float az = fmaf(byteToFloat(w1, 2), sz, bz), cz = fmaf(byteToFloat(w2, 1), sz, bz);
-            const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), tmin));
-            const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), hit.t));
-            // an empty slot is stored as lo = 255, hi = 0 on every axis and ref = kInvalid
-            const bool hitBox = (tn <= tf * 1.000001f) && (ref != kInvalid);
+            const NodeFrame F = makeNodeFrame(hdr, o, rd);
+            float tn;
+            const bool hitBox = childTest(F, sel, w1, w2, tmin, hit.t, tn) && (ref != kInvalid);
             const unsigned m = (__ballot_sync(gmask, hitBox) >> shift) & 0xffu;
             if (m) {
                 // nearest child: min over (entry distance | lane) keys; tn >= tmin >= 0 so the bits are monotone
@@ -219,6 +249,7 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
             o = xformPoint(O, T);
             d = xformVector(Dn, T);
             rd = boxRcp3(d);
+            sel = makePlaneSel(rd);
             inBlas = true;
             curInst = tail.y;
             cur = tail.x;
@@ -263,7 +294,7 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
             --sp;
             const uint2 e = stackRow[sp];
             if (e.x == kSentinel) {
-                o = O, d = Dn, rd = rdWorld;
+                o = O, d = Dn, rd = rdWorld, sel = selWorld;
                 inBlas = false;
                 continue;
             }
@@ -275,10 +306,12 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
     }
 }
 
-// ---- one ray per lane ------------------------------------------------------------------------
-// Used for the large waves (coherent camera rays and the first bounces), where 32 rays per warp
-// amortise the node decode.  "while-while" form: every lane first descends through inner nodes
-// until it holds a leaf, then the warp processes leaves together.  The stack lives in local memory.
+// ---- one ray per lane ------------------------------------------------------------------------------
+// Used for the large waves, where 32 rays per warp amortise the node decode.  "while-while" form:
+// every lane first descends through inner nodes until it holds a leaf, then the warp processes
+// leaves together.  The stack lives in local memory.  (A persistent variant that refilled finished
+// lanes from a per-warp queue slice was measured and dropped: it de-phases the lanes of coherent
+// waves and lost 2x on camera rays for a 5 % gain on diffuse bounces; see DESIGN.md.)
 struct LaneStack {
     uint2 e[kStackSize];
 };
@@ -291,32 +324,30 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
     const float tmax0 = hit.t;
     if (S.instanceCount == 0) return false;
     f3 o = O, d = Dn;
-    const f3 rdWorld = boxRcp3(Dn);
-    f3 rd = rdWorld;
+    f3 rd = boxRcp3(Dn);
+    PlaneSel sel = makePlaneSel(rd);
     bool inBlas = false;
     uint32_t curInst = 0;
     uint32_t cur = S.tlasRoot;
 
     // pops the next live entry into `cur` (kInvalid when the stack is empty)
-#define GK_POP()                                                     \
-    for (;;) {                                                       \
-        if (sp == 0) { cur = kInvalid; break; }                      \
-        --sp;                                                        \
-        const uint2 e_ = stk.e[sp];                                  \
-        if (e_.x == kSentinel) { o = O, d = Dn, rd = rdWorld, inBlas = false; continue; } \
-        if (__uint_as_float(e_.y) < hit.t) { cur = e_.x; break; }    \
+#define GK_POP()                                                                                          \
+    for (;;) {                                                                                            \
+        if (sp == 0) { cur = kInvalid; break; }                                                           \
+        --sp;                                                                                             \
+        const uint2 e_ = stk.e[sp];                                                                       \
+        if (e_.x == kSentinel) { o = O, d = Dn, rd = boxRcp3(Dn), sel = makePlaneSel(rd), inBlas = false; continue; } \
+        if (__uint_as_float(e_.y) < hit.t) { cur = e_.x; break; }                                         \
     }
 
     for (;;) {
-        // ---- (1) descend through inner nodes
+        // ---- (1) descend through inner nodes until this lane holds a leaf
         while (!(cur & kLeafBit)) {
             const uint4* np = reinterpret_cast<const uint4*>((inBlas ? S.blasNodes : S.tlasNodes) + cur);
             const uint4 hdr = __ldg(np);
             if (kStats) stats->nodeVisits++;
-            const uint32_t ec = hdr.w, count = ec >> 24;
-            const float sx = __uint_as_float((ec & 0xffu) << 23) * rd.x, sy = __uint_as_float(((ec >> 8) & 0xffu) << 23) * rd.y,
-                        sz = __uint_as_float(((ec >> 16) & 0xffu) << 23) * rd.z;
-            const float bx = (__uint_as_float(hdr.x) - o.x) * rd.x, by = (__uint_as_float(hdr.y) - o.y) * rd.y, bz = (__uint_as_float(hdr.z) - o.z) * rd.z;
+            const uint32_t count = hdr.w >> 24;
+            const NodeFrame F = makeNodeFrame(hdr, o, rd);
             float bestT = kFar;
             uint32_t bestRef = kInvalid;
 #pragma unroll
@@ -327,13 +358,9 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
                 const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t ref = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
-                    const float ax = fmaf(byteToFloat(w1, 0), sx, bx), cx = fmaf(byteToFloat(w1, 3), sx, bx);
-                    const float ay = fmaf(byteToFloat(w1, 1), sy, by), cy = fmaf(byteToFloat(w2, 0), sy, by);
-                    const float az = fmaf(byteToFloat(w1, 2), sz, bz), cz = fmaf(byteToFloat(w2, 1), sz, bz);
-                    const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), tmin));
-                    const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), hit.t));
-                    if ((tn <= tf * 1.000001f) && (ref != kInvalid)) {
+                    const uint32_t ref = w[3 * k];
+                    float tn;
+                    if (childTest(F, sel, w[3 * k + 1], w[3 * k + 2], tmin, hit.t, tn) && (ref != kInvalid)) {
                         // keep the nearest child in registers, push the other one
                         uint32_t pr = ref;
                         float pt = tn;
@@ -346,7 +373,7 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
             else { GK_POP() }
         }
         if (cur == kInvalid) break;
-        // ---- (2) leaves
+        // ---- (2) one leaf step
         if (!inBlas) {
             const uint32_t ii = cur & 0x7fffffffu;
             const float4* ip = reinterpret_cast<const float4*>(S.inst + ii);
@@ -357,6 +384,7 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
             o = xformPoint(O, T);
             d = xformVector(Dn, T);
             rd = boxRcp3(d);
+            sel = makePlaneSel(rd);
             inBlas = true;
             curInst = tail.y;
             cur = tail.x;

@@ -331,7 +331,7 @@ __global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksI
         }
         nodeSrc[(size_t)w * 8 + i] = src; // binary-tree node each slot was made from (refit re-quantises from these)
         for (int a = 0; a < 3; ++a) n.c[i].qlo[a] = 255, n.c[i].qhi[a] = 0;
-        n.c[i].pad[0] = n.c[i].pad[1] = 0;
+        n.c[i].k00 = 0x00, n.c[i].k4b = 0x4B;
     }
     uint4* o = reinterpret_cast<uint4*>(nodes + w);
     const uint4* s = reinterpret_cast<const uint4*>(&n);
@@ -346,7 +346,7 @@ __device__ __forceinline__ int chooseExponent(float lo, float hi)
     const float extent = hi - lo;
     int e = -126;
     if (extent > 0.f) {
-        const float x = extent / 250.f;
+        const float x = extent / 248.f;
         int ex = ilogbf(x);
         if (ldexpf(1.f, ex) < x) ++ex;
         e = ex;
@@ -381,7 +381,7 @@ __global__ void k_quantise(Bvh2View B, WideNode* __restrict__ nodes, const uint3
     if (nlo.x > nhi.x) nlo = nhi = make_float4(0, 0, 0, 0); // every child empty
     const int e[3] = {chooseExponent(nlo.x, nhi.x), chooseExponent(nlo.y, nhi.y), chooseExponent(nlo.z, nhi.z)};
     const float step[3] = {ldexpf(1.f, e[0]), ldexpf(1.f, e[1]), ldexpf(1.f, e[2])};
-    const float org[3] = {nlo.x - step[0], nlo.y - step[1], nlo.z - step[2]};
+    const float org[3] = {nlo.x - 2.f * step[0], nlo.y - 2.f * step[1], nlo.z - 2.f * step[2]};
     n.ox = org[0], n.oy = org[1], n.oz = org[2];
     n.ex = (uint8_t)(e[0] + 127), n.ey = (uint8_t)(e[1] + 127), n.ez = (uint8_t)(e[2] + 127);
     for (int i = 0; i < 8; ++i) {
@@ -389,7 +389,7 @@ __global__ void k_quantise(Bvh2View B, WideNode* __restrict__ nodes, const uint3
             const float l3[3] = {lo[i].x, lo[i].y, lo[i].z}, h3[3] = {hi[i].x, hi[i].y, hi[i].z};
             for (int a = 0; a < 3; ++a) {
                 // >= 1/64 step of slack on both sides: the traversal's decode error is far below it
-                const float ql = floorf((l3[a] - org[a]) / step[a] - 0.015625f), qh = ceilf((h3[a] - org[a]) / step[a] + 0.015625f);
+                const float ql = floorf((l3[a] - org[a]) / step[a] - 1.0f), qh = ceilf((h3[a] - org[a]) / step[a] + 1.0f);
                 n.c[i].qlo[a] = (uint8_t)fminf(fmaxf(ql, 0.f), 255.f);
                 n.c[i].qhi[a] = (uint8_t)fminf(fmaxf(qh, 0.f), 255.f);
             }

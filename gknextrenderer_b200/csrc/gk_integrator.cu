@@ -111,55 +111,76 @@ __global__ void __launch_bounds__(256) k_generate(const GkUniformBufferObject* _
 
 // -------------------------------------------------------------------------------- extend / shadow
 // Two mappings of rays to lanes (gk_bvh.cuh):
-//   kCoop = false : one ray per lane, 256 rays per block   (large waves)
-//   kCoop = true  : eight lanes per ray, 32 rays per block (small waves: 4-5x lower latency per ray,
+//   kCoop = false : one ray per lane, 256 rays per block (large waves)
+//   kCoop = true  : eight lanes per ray, 32 rays per block (small waves: ~5x lower latency per ray,
 //                   which is what bounds the long tail of nearly empty waves)
 __device__ __forceinline__ uint2* stackRowOf(uint2* stack) { return stack + (threadIdx.x >> 3) * kStackStride; }
 
-template <bool kAnyHit, bool kCoop, bool kStats>
-__device__ __forceinline__ bool traceQueueRay(const SceneView& V, const float4 o, const float4 d, Hit& h, uint2* stack, TraversalStats* local)
-{
-    h.t = d.w, h.u = 0, h.v = 0, h.prim = kInvalid, h.inst = kInvalid;
-    if (!(d.w > 0.0f)) return false;
-    const f3 dn = normalizeRayDir(mk3(d.x, d.y, d.z));
-    if (kCoop) return traverseCoop<kAnyHit, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, stackRowOf(stack), local);
-    return traverseLane<kAnyHit, kStats>(V, mk3(o.x, o.y, o.z), dn, o.w, h, local);
-}
-
-template <bool kCoop, bool kStats>
-__global__ void __launch_bounds__(256) k_extend(SceneView V, RayQueue Q, uint32_t count, TraversalStats* stats)
-{
-    __shared__ uint2 stack[kCoop ? kRaysPerBlock * kStackStride : 1];
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t i = kCoop ? (gt >> 3) : gt;
-    if (i >= count) return;
-    const float4 o = __ldg(Q.o_tmin + i), d = __ldg(Q.d_tmax + i);
-    Hit h;
-    TraversalStats local{0, 0};
-    traceQueueRay<false, kCoop, kStats>(V, o, d, h, stack, &local);
-    if (!kCoop || (threadIdx.x & 7u) == 0) {
+struct QueueIO { // RayIO over a RayQueue (closest hit)
+    RayQueue Q;
+    __device__ __forceinline__ bool load(uint32_t i, f3& O, f3& D, float& tmin, float& tmax) const
+    {
+        const float4 o = __ldg(Q.o_tmin + i), d = __ldg(Q.d_tmax + i);
+        O = mk3(o.x, o.y, o.z), D = mk3(d.x, d.y, d.z), tmin = o.w, tmax = d.w;
+        return d.w > 0.0f;
+    }
+    __device__ __forceinline__ void store(uint32_t i, const Hit& h, bool) const
+    {
         Q.hit_tuvp[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
         Q.hit_inst[i] = h.inst;
-        if (kStats) {
-            atomicAdd(&stats->nodeVisits, local.nodeVisits);
-            atomicAdd(&stats->triTests, local.triTests);
+    }
+};
+struct ShadowIO { // RayIO over a RayQueue (any hit: only the occlusion flag is stored)
+    RayQueue Q;
+    __device__ __forceinline__ bool load(uint32_t i, f3& O, f3& D, float& tmin, float& tmax) const
+    {
+        const float4 o = __ldg(Q.o_tmin + i), d = __ldg(Q.d_tmax + i);
+        O = mk3(o.x, o.y, o.z), D = mk3(d.x, d.y, d.z), tmin = o.w, tmax = d.w;
+        return d.w > 0.0f;
+    }
+    __device__ __forceinline__ void store(uint32_t i, const Hit&, bool occluded) const { Q.hit_inst[i] = occluded ? 1u : 0u; }
+};
+template <bool kAny> struct ArrayIO { // RayIO over interleaved {O|tmin, D|tmax} records (gk_intersect)
+    const float4* rays;
+    float* tuv;
+    uint32_t* ids;
+    __device__ __forceinline__ bool load(uint32_t i, f3& O, f3& D, float& tmin, float& tmax) const
+    {
+        const float4 o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
+        O = mk3(o.x, o.y, o.z), D = mk3(d.x, d.y, d.z), tmin = o.w, tmax = d.w;
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t i, const Hit& h, bool hit) const
+    {
+        if (tuv) tuv[3 * i] = h.t, tuv[3 * i + 1] = h.u, tuv[3 * i + 2] = h.v;
+        if (ids) {
+            if (kAny) ids[2 * i] = hit ? 1u : 0u, ids[2 * i + 1] = hit ? 1u : 0u;
+            else ids[2 * i] = h.inst == kInvalid ? kInvalid : h.prim, ids[2 * i + 1] = h.inst;
         }
     }
-}
+};
 
-template <bool kCoop, bool kStats>
-__global__ void __launch_bounds__(256) k_shadow(SceneView V, RayQueue Q, uint32_t count, TraversalStats* stats)
+// One kernel body for extend / shadow / intersect.
+template <bool kAnyHit, bool kCoop, bool kStats, class RayIO>
+__global__ void __launch_bounds__(256, kCoop ? 2 : 4) k_trace(SceneView V, RayIO io, uint32_t count, TraversalStats* stats)
 {
     __shared__ uint2 stack[kCoop ? kRaysPerBlock * kStackStride : 1];
+    TraversalStats local{0, 0};
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = kCoop ? (gt >> 3) : gt;
-    if (i >= count) return;
-    const float4 o = __ldg(Q.o_tmin + i), d = __ldg(Q.d_tmax + i);
-    Hit h;
-    TraversalStats local{0, 0};
-    const bool occluded = traceQueueRay<true, kCoop, kStats>(V, o, d, h, stack, &local);
+    if (i >= count) return; // cooperative mapping: whole 8-lane groups leave together
+    f3 O, D;
+    float tmin, tmax;
+    const bool live = io.load(i, O, D, tmin, tmax);
+    Hit h{tmax, 0.f, 0.f, kInvalid, kInvalid};
+    bool hit = false;
+    if (live) {
+        const f3 dn = normalizeRayDir(D);
+        if (kCoop) hit = traverseCoop<kAnyHit, kStats>(V, O, dn, tmin, h, stackRowOf(stack), &local);
+        else hit = traverseLane<kAnyHit, kStats>(V, O, dn, tmin, h, &local);
+    }
     if (!kCoop || (threadIdx.x & 7u) == 0) {
-        Q.hit_inst[i] = occluded ? 1u : 0u;
+        io.store(i, h, hit);
         if (kStats) {
             atomicAdd(&stats->nodeVisits, local.nodeVisits);
             atomicAdd(&stats->triTests, local.triTests);
@@ -586,47 +607,28 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams P, PathState S, 
 }
 
 // -------------------------------------------------------------------------------- utilities
-template <bool kAny, bool kCoop, bool kStats>
-__global__ void __launch_bounds__(256) k_intersect(SceneView V, const float4* __restrict__ rays, uint32_t n, float* __restrict__ tuv, uint32_t* __restrict__ ids,
-                                                   TraversalStats* stats)
+template <bool kAnyHit, class RayIO>
+static void launchTraceIO(Context& c, const SceneView& V, const RayIO& io, uint32_t count)
 {
-    __shared__ uint2 stack[kCoop ? kRaysPerBlock * kStackStride : 1];
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t i = kCoop ? (gt >> 3) : gt;
-    if (i >= n) return;
-    const float4 o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
-    Hit h;
-    TraversalStats local{0, 0};
-    const bool hit = traceQueueRay<kAny, kCoop, kStats>(V, o, d, h, stack, &local);
-    if (kCoop && (threadIdx.x & 7u) != 0) return;
-    if (tuv) tuv[3 * i] = h.t, tuv[3 * i + 1] = h.u, tuv[3 * i + 2] = h.v;
-    if (ids) {
-        if (kAny) ids[2 * i] = hit ? 1u : 0u, ids[2 * i + 1] = hit ? 1u : 0u;
-        else ids[2 * i] = h.inst == kInvalid ? kInvalid : h.prim, ids[2 * i + 1] = h.inst;
-    }
-    if (kStats) {
-        atomicAdd(&stats->nodeVisits, local.nodeVisits);
-        atomicAdd(&stats->triTests, local.triTests);
+    const bool coop = count < c.coopThreshold;
+    const unsigned per = coop ? kRaysPerBlock : 256;
+    const unsigned grid = (count + per - 1) / per;
+    cudaStream_t st = c.stream;
+    TraversalStats* ts = c.travStats ? c.dTravStats : nullptr;
+    if (coop) {
+        if (ts) k_trace<kAnyHit, true, true, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
+        else k_trace<kAnyHit, true, false, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
+    } else {
+        if (ts) k_trace<kAnyHit, false, true, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
+        else k_trace<kAnyHit, false, false, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
     }
 }
 
-// Launch helpers: pick the lane mapping by wave size.
 template <bool kShadow>
 static void launchTrace(Context& c, const SceneView& V, const RayQueue& Q, uint32_t count)
 {
-    const bool coop = count < c.coopThreshold;
-    const unsigned grid = (unsigned)((count + (coop ? kRaysPerBlock : 256) - 1) / (coop ? kRaysPerBlock : 256));
-    cudaStream_t st = c.stream;
-    TraversalStats* ts = c.travStats ? c.dTravStats : nullptr;
-#define GK_LAUNCH(K, COOP, STATS) K<COOP, STATS><<<grid, 256, 0, st>>>(V, Q, count, ts)
-    if (kShadow) {
-        if (coop) { if (ts) GK_LAUNCH(k_shadow, true, true); else GK_LAUNCH(k_shadow, true, false); }
-        else { if (ts) GK_LAUNCH(k_shadow, false, true); else GK_LAUNCH(k_shadow, false, false); }
-    } else {
-        if (coop) { if (ts) GK_LAUNCH(k_extend, true, true); else GK_LAUNCH(k_extend, true, false); }
-        else { if (ts) GK_LAUNCH(k_extend, false, true); else GK_LAUNCH(k_extend, false, false); }
-    }
-#undef GK_LAUNCH
+    if (kShadow) launchTraceIO<true>(c, V, ShadowIO{Q}, count);
+    else launchTraceIO<false>(c, V, QueueIO{Q}, count);
 }
 
 // -------------------------------------------------------------------------------- host side
@@ -859,16 +861,8 @@ GkStatus intersectDevice(Context& c, const float4* rays, uint32_t n, float* tuv,
     }
     if (n == 0) return GK_OK;
     const SceneView V = c.view();
-    const bool coop = n < c.coopThreshold;
-    const unsigned grid = (unsigned)((n + (coop ? kRaysPerBlock : 256) - 1) / (coop ? kRaysPerBlock : 256));
-    TraversalStats* ts = c.travStats ? c.dTravStats : nullptr;
-#define GK_LAUNCH(ANY, COOP, STATS) k_intersect<ANY, COOP, STATS><<<grid, 256, 0, c.stream>>>(V, rays, n, tuv, ids, ts)
-#define GK_PICK(ANY)                                                                          \
-    if (coop) { if (ts) GK_LAUNCH(ANY, true, true); else GK_LAUNCH(ANY, true, false); }       \
-    else { if (ts) GK_LAUNCH(ANY, false, true); else GK_LAUNCH(ANY, false, false); }
-    if (anyHit) { GK_PICK(true) } else { GK_PICK(false) }
-#undef GK_PICK
-#undef GK_LAUNCH
+    if (anyHit) launchTraceIO<true>(c, V, ArrayIO<true>{rays, tuv, ids}, n);
+    else launchTraceIO<false>(c, V, ArrayIO<false>{rays, tuv, ids}, n);
     GK_CUDA(cudaGetLastError());
     return GK_OK;
 }
