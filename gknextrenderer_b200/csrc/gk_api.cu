@@ -1,6 +1,7 @@
 // gk_api.cu — the extern "C" entry points declared in include/gknext_cuda.h.
 // Each function's header comment there cites the reference interface it replaces.
 #include "gk_context.h"
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -120,6 +121,7 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     c.tileIndex = cfg->tileIndex;
     c.tileRows = cfg->tileRows ? cfg->tileRows : 16;
     c.flags = cfg->flags;
+    if (const char* e = getenv("GK_BLAS_LEAF")) c.blasLeafMax = (uint32_t)std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("GK_COOP_THRESHOLD")) c.coopThreshold = (uint32_t)strtoul(e, nullptr, 10); // tuning / test hook
     if (c.tileIndex >= c.tileCount) {
         delete h;

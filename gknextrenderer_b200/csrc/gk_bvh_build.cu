@@ -607,7 +607,7 @@ GkStatus buildBlasForest(Context& c)
     if (s != GK_OK) return s;
     DevBuf<uint32_t> rootRef;
     GK_CUDA(rootRef.reserve(groups));
-    s = collapse(c, T, groups, kBlasLeafMax, false, c.dBlasNodes, c.dBlasSrc, c.blasNodeCount, rootRef.p);
+    s = collapse(c, T, groups, c.blasLeafMax, false, c.dBlasNodes, c.dBlasSrc, c.blasNodeCount, rootRef.p);
     if (s != GK_OK) return s;
     k_model_bounds_from_groups<<<gridFor(groups), 256, 0, st>>>(c.dModels.p, groups, c.dGroupLo.p, c.dGroupHi.p, rootRef.p);
     cudaEventRecord(e1, st);

@@ -147,6 +147,7 @@ struct Context {
     uint32_t* hCounts = nullptr; // pinned
     TraversalStats* dTravStats = nullptr;
     bool travStats = false;
+    uint32_t blasLeafMax = 4;       // triangles per BLAS leaf (<= kBlasLeafMax)
     uint32_t coopThreshold = 65536; // waves smaller than this use the 8-lanes-per-ray traversal
     GkFrameStats stats{};
     cudaEvent_t evA = nullptr, evB = nullptr;
