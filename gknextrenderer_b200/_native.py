@@ -113,7 +113,8 @@ class GkFrameStats(C.Structure):
     _fields_ = [("primaryRays", C.c_uint64), ("extensionRays", C.c_uint64), ("shadowRays", C.c_uint64), ("waves", C.c_uint32),
                 ("launches", C.c_uint32), ("msTotal", C.c_float), ("msBvh", C.c_float), ("msGenerate", C.c_float), ("msExtend", C.c_float),
                 ("msShade", C.c_float), ("msShadow", C.c_float), ("msAccumulate", C.c_float), ("msReproject", C.c_float),
-                ("msDenoise", C.c_float), ("nodeVisits", C.c_uint64), ("triTests", C.c_uint64)]
+                ("msDenoise", C.c_float), ("nodeVisits", C.c_uint64), ("triTests", C.c_uint64),
+                ("tlasVisits", C.c_uint64), ("instanceEntries", C.c_uint64)]
 
 
 class GkBvhInfo(C.Structure):

@@ -122,6 +122,7 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     c.tileRows = cfg->tileRows ? cfg->tileRows : 16;
     c.flags = cfg->flags;
     if (const char* e = getenv("GK_BLAS_LEAF")) c.blasLeafMax = (uint32_t)std::min(8, std::max(1, atoi(e)));
+    if (const char* e = getenv("GK_SAH_COLLAPSE")) c.sahCollapse = atoi(e) != 0;
     if (const char* e = getenv("GK_COOP_THRESHOLD")) c.coopThreshold = (uint32_t)strtoul(e, nullptr, 10); // tuning / test hook
     if (c.tileIndex >= c.tileCount) {
         delete h;
@@ -393,7 +394,7 @@ GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out)
     if (c.travStats) {
         TraversalStats h;
         GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));
-        c.stats.nodeVisits = h.nodeVisits, c.stats.triTests = h.triTests;
+        c.stats.nodeVisits = h.nodeVisits, c.stats.triTests = h.triTests, c.stats.tlasVisits = h.tlasVisits, c.stats.instanceEntries = h.instanceEntries;
     }
     *out = c.stats;
     return GK_OK;

@@ -94,7 +94,7 @@ struct Hit {
 };
 
 struct TraversalStats {
-    unsigned long long nodeVisits, triTests;
+    unsigned long long nodeVisits, triTests, tlasVisits, instanceEntries;
 };
 
 // ---- exact triangle test -------------------------------------------------------------
@@ -218,7 +218,7 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
             const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(N));
             const uint32_t* cw = reinterpret_cast<const uint32_t*>(N) + 4 + 3 * sub;
             const uint32_t ref = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2);
-            if (kStats && sub == 0) stats->nodeVisits++;
+            if (kStats && sub == 0) { stats->nodeVisits++; if (!inBlas) stats->tlasVisits++; }
             const NodeFrame F = makeNodeFrame(hdr, o, rd);
             float tn;
             const bool hitBox = childTest(F, sel, w1, w2, tmin, hit.t, tn) && (ref != kInvalid);
@@ -244,6 +244,7 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
             const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
             const uint4 tail = __ldg(reinterpret_cast<const uint4*>(ip + 4));
             const float T[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+            if (kStats && sub == 0) stats->instanceEntries++;
             if (sub == 0 && sp < kStackSize) stackRow[sp] = make_uint2(kSentinel, 0u);
             sp = min(sp + 1, kStackSize);
             o = xformPoint(O, T);
@@ -345,7 +346,7 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
         while (!(cur & kLeafBit)) {
             const uint4* np = reinterpret_cast<const uint4*>((inBlas ? S.blasNodes : S.tlasNodes) + cur);
             const uint4 hdr = __ldg(np);
-            if (kStats) stats->nodeVisits++;
+            if (kStats) { stats->nodeVisits++; if (!inBlas) stats->tlasVisits++; }
             const uint32_t count = hdr.w >> 24;
             const NodeFrame F = makeNodeFrame(hdr, o, rd);
             float bestT = kFar;
@@ -380,6 +381,7 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
             const float4 r0 = __ldg(ip), r1 = __ldg(ip + 1), r2 = __ldg(ip + 2), r3 = __ldg(ip + 3);
             const uint4 tail = __ldg(reinterpret_cast<const uint4*>(ip + 4));
             const float T[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+            if (kStats) stats->instanceEntries++;
             if (sp < kStackSize) stk.e[sp++] = make_uint2(kSentinel, 0u);
             o = xformPoint(O, T);
             d = xformVector(Dn, T);
@@ -412,6 +414,7 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
 #undef GK_POP
     return hit.t < tmax0;
 }
+
 #endif // __CUDACC__
 
 } // namespace gk

@@ -160,8 +160,24 @@ __global__ void k_leaf_boxes(const float4* __restrict__ plo, const float4* __res
     llo[k] = plo[p], lhi[k] = phi[p];
 }
 
+// Cost model of the wide collapse (node visit = 1): one triangle test, one instance entry.
+constexpr float kCostTri = 0.3f;
+constexpr float kCostInstance = 1.5f;
+
+__device__ __forceinline__ float boxAreaOrZero(float lx, float ly, float lz, float hx, float hy, float hz)
+{
+    if (lx > hx) return 0.f; // empty box (hidden instance)
+    const float ex = hx - lx, ey = hy - ly, ez = hz - lz;
+    return ex * ey + ey * ez + ez * ex;
+}
+
+// Bottom-up: boxes of the internal nodes and, when `cost` is given, the collapse cost table of
+// Ylitie et al. 2017 ("Efficient incoherent ray traversal on GPUs through compressed wide BVHs", 3.1):
+// cost[8*n + i-1] = cheapest SAH cost of representing the subtree of n with at most i slots of
+// its parent's wide node (i = 1..7); slot [7] holds the cost of n as a wide node of its own.
 __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right, const uint32_t* __restrict__ parentI,
-                                   const uint32_t* __restrict__ parentL, const float4* llo, const float4* lhi, float4* ilo, float4* ihi, int* flags)
+                                   const uint32_t* __restrict__ parentL, const float4* llo, const float4* lhi, float4* ilo, float4* ihi, int* flags,
+                                   float* cost, const uint32_t* __restrict__ first, const uint32_t* __restrict__ last, uint32_t leafMax, float primCost)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n || n < 2) return;
@@ -174,9 +190,53 @@ __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left
         const volatile float4* ph0 = (L & kLeafBit) ? lhi + (L & 0x7fffffffu) : ihi + L;
         const volatile float4* pl1 = (R & kLeafBit) ? llo + (R & 0x7fffffffu) : ilo + R;
         const volatile float4* ph1 = (R & kLeafBit) ? lhi + (R & 0x7fffffffu) : ihi + R;
-        const float lx = fminf(pl0->x, pl1->x), ly = fminf(pl0->y, pl1->y), lz = fminf(pl0->z, pl1->z);
-        const float hx = fmaxf(ph0->x, ph1->x), hy = fmaxf(ph0->y, ph1->y), hz = fmaxf(ph0->z, ph1->z);
+        const float l0x = pl0->x, l0y = pl0->y, l0z = pl0->z, h0x = ph0->x, h0y = ph0->y, h0z = ph0->z;
+        const float l1x = pl1->x, l1y = pl1->y, l1z = pl1->z, h1x = ph1->x, h1y = ph1->y, h1z = ph1->z;
+        const float lx = fminf(l0x, l1x), ly = fminf(l0y, l1y), lz = fminf(l0z, l1z);
+        const float hx = fmaxf(h0x, h1x), hy = fmaxf(h0y, h1y), hz = fmaxf(h0z, h1z);
         ilo[cur] = make_float4(lx, ly, lz, 0), ihi[cur] = make_float4(hx, hy, hz, 0);
+        if (cost) {
+            float cl[7], cr[7];
+            if (L & kLeafBit) {
+                const float a = boxAreaOrZero(l0x, l0y, l0z, h0x, h0y, h0z) * primCost;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) cl[i] = a;
+            } else {
+                const volatile float* c = cost + 8 * (size_t)L;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) cl[i] = c[i];
+            }
+            if (R & kLeafBit) {
+                const float a = boxAreaOrZero(l1x, l1y, l1z, h1x, h1y, h1z) * primCost;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) cr[i] = a;
+            } else {
+                const volatile float* c = cost + 8 * (size_t)R;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) cr[i] = c[i];
+            }
+            float D[9]; // D[j]: children of `cur` spread over j slots
+#pragma unroll
+            for (int j = 2; j <= 8; ++j) {
+                float best = kFar;
+#pragma unroll
+                for (int a = 1; a < j; ++a) best = fminf(best, cl[a - 1] + cr[j - a - 1]);
+                D[j] = best;
+            }
+            const float A = boxAreaOrZero(lx, ly, lz, hx, hy, hz);
+            const uint32_t P = last[cur] - first[cur] + 1;
+            const float asNode = D[8] + A;
+            const float asLeaf = (P <= leafMax) ? A * (float)P * primCost : kFar;
+            float* o = cost + 8 * (size_t)cur;
+            float prev = fminf(asLeaf, asNode);
+            o[0] = prev;
+#pragma unroll
+            for (int i = 2; i <= 7; ++i) {
+                prev = fminf(D[i], prev);
+                o[i - 1] = prev;
+            }
+            o[7] = asNode;
+        }
         cur = parentI[cur];
     }
 }
@@ -221,6 +281,8 @@ __global__ void k_write_tri_records(const float4* __restrict__ triP, const uint3
 struct Bvh2View {
     const uint32_t *left, *right, *first, *last, *order;
     const float4 *ilo, *ihi, *llo, *lhi;
+    const float* cost; // collapse cost table (null: greedy surface-area collapse)
+    float primCost;
 };
 
 __device__ __forceinline__ float boxArea(float4 lo, float4 hi)
@@ -238,7 +300,9 @@ __device__ __forceinline__ uint32_t finalLeafRef(const Bvh2View& B, uint32_t ref
         return tlas ? (kLeafBit | B.order[k]) : (kLeafBit | (k << 3));
     }
     const uint32_t size = B.last[ref] - B.first[ref] + 1;
-    if (!tlas && size <= leafMax) {
+    bool asLeaf = !tlas && size <= leafMax;
+    if (asLeaf && B.cost) asLeaf = boxArea(B.ilo[ref], B.ihi[ref]) * (float)size * B.primCost <= B.cost[8 * (size_t)ref + 7];
+    if (asLeaf) {
         isLeaf = true;
         return kLeafBit | (B.first[ref] << 3) | (size - 1);
     }
@@ -277,7 +341,49 @@ __global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksI
     if (ti >= taskCount) return;
     const uint32_t b2 = tasksIn[2 * ti], w = tasksIn[2 * ti + 1];
     uint32_t slot[8];
-    int cnt = 2;
+    int cnt = 0;
+    if (B.cost) {
+        // spread the subtree of b2 over the eight slots as the cost table dictates (left to right)
+        uint32_t stRef[16];
+        int stBudget[16];
+        int sp = 0;
+        stRef[sp] = b2, stBudget[sp] = 9, ++sp; // 9: "open this node over 8 slots"
+        while (sp) {
+            --sp;
+            const uint32_t m = stRef[sp];
+            int budget = stBudget[sp];
+            if ((m & kLeafBit) || budget == 1) {
+                slot[cnt++] = m;
+                continue;
+            }
+            if (budget == 9) budget = 8;
+            else {
+                // fewer slots cost the same: hand the budget down (table entries are running minima)
+                const float* cm = B.cost + 8 * (size_t)m;
+                while (budget > 1 && cm[budget - 1] == cm[budget - 2]) --budget;
+                if (budget == 1) {
+                    slot[cnt++] = m;
+                    continue;
+                }
+            }
+            const uint32_t L = B.left[m], R = B.right[m];
+            float cl[7], cr[7];
+            if (L & kLeafBit) for (int i = 0; i < 7; ++i) cl[i] = 0.f;
+            else for (int i = 0; i < 7; ++i) cl[i] = B.cost[8 * (size_t)L + i];
+            if (R & kLeafBit) for (int i = 0; i < 7; ++i) cr[i] = 0.f;
+            else for (int i = 0; i < 7; ++i) cr[i] = B.cost[8 * (size_t)R + i];
+            int bestA = 1;
+            float best = kFar;
+            for (int a = 1; a < budget; ++a) {
+                const float v = cl[a - 1] + cr[budget - a - 1];
+                if (v < best) best = v, bestA = a;
+            }
+            // right first so that the left subtree is emitted first
+            stRef[sp] = R, stBudget[sp] = budget - bestA, ++sp;
+            stRef[sp] = L, stBudget[sp] = bestA, ++sp;
+        }
+    } else {
+    cnt = 2;
     slot[0] = B.left[b2], slot[1] = B.right[b2];
     // greedy: open the internal child with the largest box until 8 slots are used
     for (;;) {
@@ -297,6 +403,7 @@ __global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksI
         for (int i = cnt; i > best + 1; --i) slot[i] = slot[i - 1];
         slot[best] = B.left[r], slot[best + 1] = B.right[r];
         ++cnt;
+    }
     }
     uint32_t refs[8];
     bool leaf[8];
@@ -484,7 +591,7 @@ __global__ void k_model_bounds_from_groups(ModelInfo* models, uint32_t modelCoun
 void Lbvh::release()
 {
     keys.release(), keysAlt.release(), order.release(), orderAlt.release(), left.release(), right.release(), parentI.release(), parentL.release();
-    first.release(), last.release(), ilo.release(), ihi.release(), llo.release(), lhi.release(), plo.release(), phi.release(), group.release(), flags.release();
+    first.release(), last.release(), cost.release(), ilo.release(), ihi.release(), llo.release(), lhi.release(), plo.release(), phi.release(), group.release(), flags.release();
 }
 
 static inline unsigned gridFor(size_t n, unsigned block = 256) { return (unsigned)((n + block - 1) / block); }
@@ -524,14 +631,19 @@ static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint3
     return GK_OK;
 }
 
-static GkStatus propagateBounds(Context& c, Lbvh& T)
+static GkStatus propagateBounds(Context& c, Lbvh& T, bool withCost, uint32_t leafMax, float primCost)
 {
     const uint32_t n = T.n;
     cudaStream_t st = c.stream;
     k_leaf_boxes<<<gridFor(n), 256, 0, st>>>(T.plo.p, T.phi.p, T.order.p, n, T.llo.p, T.lhi.p);
+    T.costValid = false;
     if (n > 1) {
+        if (withCost) GK_CUDA(T.cost.reserve(8 * (size_t)n));
         GK_CUDA(cudaMemsetAsync(T.flags.p, 0, sizeof(int) * n, st));
-        k_propagate_bounds<<<gridFor(n), 256, 0, st>>>(n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, T.llo.p, T.lhi.p, T.ilo.p, T.ihi.p, T.flags.p);
+        k_propagate_bounds<<<gridFor(n), 256, 0, st>>>(n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, T.llo.p, T.lhi.p, T.ilo.p, T.ihi.p, T.flags.p,
+                                                       withCost ? T.cost.p : nullptr, T.first.p, T.last.p, leafMax, primCost);
+        T.costValid = withCost;
+        T.primCost = primCost;
     }
     GK_CUDA(cudaGetLastError());
     return GK_OK;
@@ -542,6 +654,7 @@ static Bvh2View viewOf(const Lbvh& T)
     Bvh2View B;
     B.left = T.left.p, B.right = T.right.p, B.first = T.first.p, B.last = T.last.p, B.order = T.order.p;
     B.ilo = T.ilo.p, B.ihi = T.ihi.p, B.llo = T.llo.p, B.lhi = T.lhi.p;
+    B.cost = T.costValid ? T.cost.p : nullptr, B.primCost = T.primCost;
     return B;
 }
 
@@ -603,7 +716,7 @@ GkStatus buildBlasForest(Context& c)
     if (s != GK_OK) return s;
     GK_CUDA(c.dTris.reserve(T.n));
     k_write_tri_records<<<gridFor(T.n), 256, 0, st>>>(sceneTriPositions().p, T.order.p, c.dModels.p, T.group.p, T.n, c.dTris.p);
-    s = propagateBounds(c, T);
+    s = propagateBounds(c, T, c.sahCollapse, c.blasLeafMax, kCostTri);
     if (s != GK_OK) return s;
     DevBuf<uint32_t> rootRef;
     GK_CUDA(rootRef.reserve(groups));
@@ -648,7 +761,7 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
         s = buildRadixTree(c, T, nullptr, 1, 42);
         if (s != GK_OK) return s;
     }
-    s = propagateBounds(c, T);
+    s = propagateBounds(c, T, c.sahCollapse && !refit, 0, kCostInstance);
     if (s != GK_OK) return s;
     if (!refit) {
         DevBuf<uint32_t> rootRef;

@@ -54,6 +54,9 @@ struct Lbvh {
     DevBuf<float4> plo, phi;           // primitive boxes in primitive order
     DevBuf<uint32_t> group;            // primitive -> group (model) id
     DevBuf<int> flags;
+    DevBuf<float> cost;                // collapse cost table, 8 floats per internal node (build only)
+    bool costValid = false;
+    float primCost = 1.f;
     void release();
 };
 
@@ -153,6 +156,7 @@ struct Context {
     cudaEvent_t evA = nullptr, evB = nullptr;
     std::vector<cudaEvent_t> evPool;
     int captureWave = -1;
+    bool sahCollapse = true;        // cost-driven wide collapse (false: greedy by surface area)
     DevBuf<float4> dCapture;
     uint32_t capturedCount = 0;
     uint64_t frameIndex = 0;

@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(256, kCoop ? 2 : 4) k_trace(SceneView V, RayIO
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = kCoop ? (gt >> 3) : gt;
     if (i >= count) return; // cooperative mapping: whole 8-lane groups leave together
-    f3 O, D;
-    float tmin, tmax;
+    f3 O = mk3(0, 0, 0), D = mk3(0, 0, 1);
+    float tmin = 0.f, tmax = 0.f;
     const bool live = io.load(i, O, D, tmin, tmax);
     Hit h{tmax, 0.f, 0.f, kInvalid, kInvalid};
     bool hit = false;
@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(256, kCoop ? 2 : 4) k_trace(SceneView V, RayIO
         if (kStats) {
             atomicAdd(&stats->nodeVisits, local.nodeVisits);
             atomicAdd(&stats->triTests, local.triTests);
+            atomicAdd(&stats->tlasVisits, local.tlasVisits);
+            atomicAdd(&stats->instanceEntries, local.instanceEntries);
         }
     }
 }
@@ -607,21 +609,22 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams P, PathState S, 
 }
 
 // -------------------------------------------------------------------------------- utilities
+template <bool kAnyHit, bool kCoop, class RayIO>
+static void launchMapped(cudaStream_t st, unsigned grid, const SceneView& V, const RayIO& io, uint32_t count, TraversalStats* ts)
+{
+    if (ts) k_trace<kAnyHit, kCoop, true, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
+    else k_trace<kAnyHit, kCoop, false, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
+}
+
 template <bool kAnyHit, class RayIO>
 static void launchTraceIO(Context& c, const SceneView& V, const RayIO& io, uint32_t count)
 {
     const bool coop = count < c.coopThreshold;
     const unsigned per = coop ? kRaysPerBlock : 256;
     const unsigned grid = (count + per - 1) / per;
-    cudaStream_t st = c.stream;
     TraversalStats* ts = c.travStats ? c.dTravStats : nullptr;
-    if (coop) {
-        if (ts) k_trace<kAnyHit, true, true, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
-        else k_trace<kAnyHit, true, false, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
-    } else {
-        if (ts) k_trace<kAnyHit, false, true, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
-        else k_trace<kAnyHit, false, false, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
-    }
+    if (coop) launchMapped<kAnyHit, true>(c.stream, grid, V, io, count, ts);
+    else launchMapped<kAnyHit, false>(c.stream, grid, V, io, count, ts);
 }
 
 template <bool kShadow>
@@ -848,7 +851,7 @@ GkStatus traceFrame(Context& c)
     if (c.travStats) {
         TraversalStats h;
         GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));
-        fs.nodeVisits = h.nodeVisits, fs.triTests = h.triTests;
+        fs.nodeVisits = h.nodeVisits, fs.triTests = h.triTests, fs.tlasVisits = h.tlasVisits, fs.instanceEntries = h.instanceEntries;
     }
     return GK_OK;
 }

@@ -93,6 +93,7 @@ typedef struct GkFrameStats {
     float msGenerate, msExtend, msShade, msShadow, msAccumulate; /* integrator */
     float msReproject, msDenoise;
     uint64_t nodeVisits, triTests; /* only when traversal statistics are enabled */
+    uint64_t tlasVisits, instanceEntries; /* ditto: node visits in the TLAS, ray -> instance transitions */
 } GkFrameStats;
 
 typedef struct GkBvhInfo {
