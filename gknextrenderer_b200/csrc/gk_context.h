@@ -149,6 +149,8 @@ struct Context {
     std::vector<void*> queueAllocs;
     uint32_t* hCounts = nullptr; // pinned
     TraversalStats* dTravStats = nullptr;
+    unsigned long long* dTailCounters = nullptr;
+    uint32_t tailThreshold = 0;     // finish the frame in one launch once this few paths are alive (0: never)
     bool travStats = false;
     uint32_t blasLeafMax = 4;       // triangles per BLAS leaf (<= kBlasLeafMax)
     uint32_t coopThreshold = 65536; // waves smaller than this use the 8-lanes-per-ray traversal

@@ -233,19 +233,34 @@ __device__ __forceinline__ void setupBounce(const ShadeScene& SS, u4& rng, const
     e.tmin = kEps, e.tmax = kMaxTrace;
 }
 
-__global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, ShadeScene SS, PathState S, PlaneView PL, RayQueue inE,
-                                               uint32_t countE, RayQueue inS, uint32_t countS, RayQueue outE, RayQueue outS)
+// What a path needs to know about the ray it was waiting for.
+struct QueueSrc { // results sitting in the wave's queues
+    RayQueue inE, inS;
+    uint32_t slot;
+    __device__ __forceinline__ float4 hitTuvp() const { return inE.hit_tuvp[slot]; }
+    __device__ __forceinline__ uint32_t hitInst() const { return inE.hit_inst[slot]; }
+    __device__ __forceinline__ float4 rayO() const { return inE.o_tmin[slot]; }
+    __device__ __forceinline__ float4 rayD() const { return inE.d_tmax[slot]; }
+    __device__ __forceinline__ bool occluded() const { return inS.hit_inst[slot] != 0; }
+};
+struct RegSrc { // results held in registers (tail kernel)
+    float4 o, d, tuvp;
+    uint32_t inst;
+    bool occ;
+    __device__ __forceinline__ float4 hitTuvp() const { return tuvp; }
+    __device__ __forceinline__ uint32_t hitInst() const { return inst; }
+    __device__ __forceinline__ float4 rayO() const { return o; }
+    __device__ __forceinline__ float4 rayD() const { return d; }
+    __device__ __forceinline__ bool occluded() const { return occ; }
+};
+
+// One step of a path's state machine: consume the result of its outstanding ray, run the control
+// flow of FPathTracingRenderer::Render up to the next ray (returned in `e`) or to the end of the path.
+template <class Src>
+__device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const FrameParams& P, const ShadeScene& SS, const PathState& S, const PlaneView& PL,
+                                          uint32_t path, const Src& src, Emit& e)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < countE + countS;
-    Emit e;
-    e.kind = 0;
-    uint32_t path = 0;
-    if (active) {
-        const GkUniformBufferObject& U = *ubo;
-        const bool fromExtend = i < countE;
-        const uint32_t slot = fromExtend ? i : i - countE;
-        path = fromExtend ? inE.path[slot] : inS.path[slot];
+    {
         const float4 nf = S.nrmFlags[path];
         uint32_t flags = __float_as_uint(nf.w);
         uint32_t state = flagsState(flags);
@@ -292,8 +307,8 @@ __global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __re
             if (state == ST_PRIMARY || state == ST_PRIMARY_DOF) {
                 // ---- Core.PathTracing main :46-79 with FVisibilityBufferRayCaster (Shading.slang:287-434);
                 //      the visibility id comes from the traced primary ray instead of the raster pass.
-                const float4 hr = inE.hit_tuvp[slot];
-                const uint32_t hinst = inE.hit_inst[slot], hprim = __float_as_uint(hr.w);
+                const float4 hr = src.hitTuvp();
+                const uint32_t hinst = src.hitInst(), hprim = __float_as_uint(hr.w);
                 const uint32_t py = pixel / P.width, px = pixel - py * P.width;
                 const f3 rayDir0 = cameraDir(U, (int)px, (int)py, P.width, P.height);
                 bool resolved = false;
@@ -426,12 +441,12 @@ __global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __re
                 loadPrimary();
                 loadAcc();
                 loadCurrent();
-                const float4 hr = inE.hit_tuvp[slot];
-                const uint32_t hinst = inE.hit_inst[slot];
+                const float4 hr = src.hitTuvp();
+                const uint32_t hinst = src.hitInst();
                 const uint32_t maxBounces = (bits & F_PRIM_DIELECTRIC) ? U.MaxNumberOfBounces : U.NumberOfBounces;
                 bool terminated;
                 if (hinst != kInvalid) {
-                    const float4 ro = inE.o_tmin[slot], rd = inE.d_tmax[slot];
+                    const float4 ro = src.rayO(), rd = src.rayD();
                     Vtx hv;
                     resolveHit(SS, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), hr.x, hr.y, hr.z, __float_as_uint(hr.w), hinst, hv);
                     vpos = hv.Position, vnrm = hv.Normal, vmat = hv.MaterialIndex;
@@ -463,7 +478,7 @@ __global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __re
                 loadPrimary();
                 loadAcc();
                 loadCurrent();
-                const bool occluded = inS.hit_inst[slot] != 0;
+                const bool occluded = src.occluded();
                 if (!occluded) {
                     color = color * mk3(U.SunColor[0], U.SunColor[1], U.SunColor[2]);
                     phase = PH_END_SAMPLE;
@@ -471,7 +486,7 @@ __global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __re
             } else if (state == ST_DIRECT) {
                 loadPrimary();
                 loadAcc();
-                shadowTerm = inS.hit_inst[slot] != 0 ? 0.f : 1.f;
+                shadowTerm = src.occluded() ? 0.f : 1.f;
                 phase = PH_FINAL;
             }
 
@@ -559,36 +574,86 @@ __global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __re
         }
     }
 
-    // ---- append to the next wave's queues: one atomic per warp and queue
+}
+
+// Appends the rays of a warp to the next wave's queues: one atomic per warp and queue.
+__device__ __forceinline__ void appendRay(const Emit& e, uint32_t path, const RayQueue& outE, const RayQueue& outS)
+{
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
-    {
-        const unsigned m = __ballot_sync(full, e.kind == 1);
+#pragma unroll
+    for (int kind = 1; kind <= 2; ++kind) {
+        const RayQueue& Q = kind == 1 ? outE : outS;
+        const unsigned m = __ballot_sync(full, e.kind == kind);
         if (m) {
             uint32_t base = 0;
-            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(outE.count, (uint32_t)__popc(m));
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(Q.count, (uint32_t)__popc(m));
             base = __shfl_sync(full, base, __ffs(m) - 1);
-            if (e.kind == 1) {
+            if (e.kind == kind) {
                 const uint32_t dst = base + __popc(m & ((1u << lane) - 1u));
-                outE.o_tmin[dst] = make_float4(e.o.x, e.o.y, e.o.z, e.tmin);
-                outE.d_tmax[dst] = make_float4(e.d.x, e.d.y, e.d.z, e.tmax);
-                outE.path[dst] = path;
+                Q.o_tmin[dst] = make_float4(e.o.x, e.o.y, e.o.z, e.tmin);
+                Q.d_tmax[dst] = make_float4(e.d.x, e.d.y, e.d.z, e.tmax);
+                Q.path[dst] = path;
             }
         }
     }
-    {
-        const unsigned m = __ballot_sync(full, e.kind == 2);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(outS.count, (uint32_t)__popc(m));
-            base = __shfl_sync(full, base, __ffs(m) - 1);
-            if (e.kind == 2) {
-                const uint32_t dst = base + __popc(m & ((1u << lane) - 1u));
-                outS.o_tmin[dst] = make_float4(e.o.x, e.o.y, e.o.z, e.tmin);
-                outS.d_tmax[dst] = make_float4(e.d.x, e.d.y, e.d.z, e.tmax);
-                outS.path[dst] = path;
+}
+
+__global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, ShadeScene SS, PathState S, PlaneView PL, RayQueue inE,
+                                               uint32_t countE, RayQueue inS, uint32_t countS, RayQueue outE, RayQueue outS)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    Emit e;
+    e.kind = 0;
+    uint32_t path = 0;
+    if (i < countE + countS) {
+        const bool fromExtend = i < countE;
+        const uint32_t slot = fromExtend ? i : i - countE;
+        path = fromExtend ? inE.path[slot] : inS.path[slot];
+        shadePath(*ubo, P, SS, S, PL, path, QueueSrc{inE, inS, slot}, e);
+    }
+    appendRay(e, path, outE, outS);
+}
+
+// Tail of the frame: when few paths are still alive, one launch walks every one of them to its end
+// (trace -> shade -> trace ...), one path per lane, instead of paying three launches and a queue
+// count read-back per wave.  counters[0] / [1] receive the extension / shadow rays traced here.
+__global__ void __launch_bounds__(128, 4) k_tail(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, SceneView V, ShadeScene SS, PathState S, PlaneView PL,
+                                                 RayQueue inE, uint32_t countE, RayQueue inS, uint32_t countS, unsigned long long* __restrict__ counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nE = 0, nS = 0;
+    if (i < countE + countS) {
+        const bool fromExtend = i < countE;
+        const uint32_t slot = fromExtend ? i : i - countE;
+        const RayQueue& Q = fromExtend ? inE : inS;
+        const uint32_t path = Q.path[slot];
+        RegSrc r;
+        r.o = Q.o_tmin[slot], r.d = Q.d_tmax[slot];
+        int kind = fromExtend ? 1 : 2;
+        for (int guard = 0; guard < 65536 && kind != 0; ++guard) {
+            Hit h{r.d.w, 0.f, 0.f, kInvalid, kInvalid};
+            bool hit = false;
+            if (r.d.w > 0.0f) {
+                const f3 O = mk3(r.o.x, r.o.y, r.o.z), dn = normalizeRayDir(mk3(r.d.x, r.d.y, r.d.z));
+                if (kind == 1) hit = traverseLane<false, false>(V, O, dn, r.o.w, h, nullptr), ++nE;
+                else hit = traverseLane<true, false>(V, O, dn, r.o.w, h, nullptr), ++nS;
             }
+            r.tuvp = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            r.inst = h.inst;
+            r.occ = hit;
+            Emit e;
+            e.kind = 0;
+            shadePath(*ubo, P, SS, S, PL, path, r, e);
+            kind = e.kind;
+            r.o = make_float4(e.o.x, e.o.y, e.o.z, e.tmin), r.d = make_float4(e.d.x, e.d.y, e.d.z, e.tmax);
         }
+    }
+    const unsigned full = 0xffffffffu;
+    for (int o = 16; o; o >>= 1) nE += __shfl_xor_sync(full, nE, o), nS += __shfl_xor_sync(full, nS, o);
+    if ((threadIdx.x & 31u) == 0) {
+        if (nE) atomicAdd(&counters[0], (unsigned long long)nE);
+        if (nS) atomicAdd(&counters[1], (unsigned long long)nS);
     }
 }
 
@@ -663,6 +728,8 @@ void freeFrameResources(Context& c)
     c.hCounts = nullptr;
     if (c.dTravStats) cudaFree(c.dTravStats);
     c.dTravStats = nullptr;
+    if (c.dTailCounters) cudaFree(c.dTailCounters);
+    c.dTailCounters = nullptr;
 }
 
 static size_t planePixelBytes(int plane)
@@ -723,6 +790,7 @@ GkStatus allocFrameResources(Context& c)
     }
     GK_CUDA(cudaMalloc(&c.dUbo, sizeof(GkUniformBufferObject)));
     GK_CUDA(cudaMallocHost(&c.hCounts, 64));
+    GK_CUDA(cudaMalloc(&c.dTailCounters, 2 * sizeof(unsigned long long)));
     GK_CUDA(cudaMalloc(&c.dTravStats, sizeof(TraversalStats)));
     GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), c.stream));
     GK_CUDA(cudaStreamSynchronize(c.stream));
@@ -776,7 +844,7 @@ GkStatus traceFrame(Context& c)
     GkFrameStats& fs = c.stats;
     fs.primaryRays = fs.extensionRays = fs.shadowRays = 0;
     fs.waves = fs.launches = 0;
-    fs.msGenerate = fs.msExtend = fs.msShade = fs.msShadow = fs.msAccumulate = 0;
+    fs.msGenerate = fs.msExtend = fs.msShade = fs.msShadow = fs.msAccumulate = fs.msTail = 0;
     size_t ev = 0;
     struct Span { size_t a, b; int kind; };
     std::vector<Span> spans;
@@ -792,10 +860,26 @@ GkStatus traceFrame(Context& c)
     const size_t evGen = mark();
     spans.push_back({evStart, evGen, 0});
     uint32_t countE = n, countS = 0;
+    bool tailRan = false;
+    fs.tailPaths = 0;
     fs.primaryRays = (uint64_t)c.ownedRows * c.width;
     c.capturedCount = 0;
     for (uint32_t wave = 0; wave < 4096; ++wave) {
         if (countE == 0 && countS == 0) break;
+        if (wave > 0 && countE + countS <= c.tailThreshold && !c.travStats && c.captureWave < 0) {
+            // few paths left: finish them in one launch
+            const size_t a = mark();
+            GK_CUDA(cudaMemsetAsync(c.dTailCounters, 0, 2 * sizeof(unsigned long long), st));
+            k_tail<<<gridFor((size_t)countE + countS, 128), 128, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.dTailCounters);
+            fs.launches++;
+            const size_t b = mark();
+            spans.push_back({a, b, 5});
+            GK_CUDA(cudaMemcpyAsync(c.hCounts + 2, c.dTailCounters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            fs.tailPaths = countE + countS;
+            tailRan = true;
+            fs.waves++;
+            break;
+        }
         const size_t a = mark();
         if (countE) {
             if ((int)wave == c.captureWave) {
@@ -845,9 +929,15 @@ GkStatus traceFrame(Context& c)
         else if (s.kind == 1) fs.msExtend += ms;
         else if (s.kind == 2) fs.msShadow += ms;
         else if (s.kind == 3) fs.msShade += ms;
+        else if (s.kind == 5) fs.msTail += ms;
         else fs.msAccumulate += ms;
     }
     cudaEventElapsedTime(&fs.msTotal, c.evPool[evStart], c.evPool[hEnd]);
+    if (tailRan) {
+        unsigned long long t[2];
+        memcpy(t, c.hCounts + 2, sizeof(t));
+        fs.extensionRays += t[0], fs.shadowRays += t[1];
+    }
     if (c.travStats) {
         TraversalStats h;
         GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));

@@ -94,6 +94,8 @@ typedef struct GkFrameStats {
     float msReproject, msDenoise;
     uint64_t nodeVisits, triTests; /* only when traversal statistics are enabled */
     uint64_t tlasVisits, instanceEntries; /* ditto: node visits in the TLAS, ray -> instance transitions */
+    float msTail;       /* the single launch that finishes the last paths of the frame */
+    uint32_t tailPaths; /* paths alive when that launch started */
 } GkFrameStats;
 
 typedef struct GkBvhInfo {
