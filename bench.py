@@ -193,7 +193,7 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = dict(rays=0, launches=0, ext=0.0, shd=0.0, shade=0.0, gen=0.0, acc=0.0, rep=0.0, jbf=0.0, bvh=0.0, eray=0, sray=0, pray=0, waves=0)
+    agg = dict(rays=0, launches=0, ext=0.0, shd=0.0, shade=0.0, gen=0.0, acc=0.0, rep=0.0, jbf=0.0, bvh=0.0, eray=0, sray=0, pray=0, waves=0, tail=0.0, tail_eray=0, tail_paths=0, ext_launches=0)
     e0.record(stream)
     t_wall = time.perf_counter()
     for i in range(args.steps):
@@ -202,6 +202,7 @@ def main():
         agg["ext"] += st.msExtend; agg["shd"] += st.msShadow; agg["shade"] += st.msShade; agg["gen"] += st.msGenerate; agg["acc"] += st.msAccumulate
         agg["rep"] += st.msReproject; agg["jbf"] += st.msDenoise; agg["bvh"] += st.msBvh if dynamic else 0.0
         agg["eray"] += st.extensionRays; agg["sray"] += st.shadowRays; agg["pray"] += st.primaryRays; agg["waves"] += st.waves
+        agg["tail"] += st.msTail; agg["tail_eray"] += st.tailExtensionRays; agg["tail_paths"] += st.tailPaths; agg["ext_launches"] += st.waves - (1 if st.tailPaths else 0)
     e1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
@@ -255,7 +256,7 @@ def main():
     nodes_per_ray = st1.nodeVisits / max(traced, 1)
     tris_per_ray = st1.triTests / max(traced, 1)
     bytes_per_ray = 48.0 + 128.0 * nodes_per_ray + 48.0 * tris_per_ray  # ray 32 + hit 16, 128-B node lines, 48-B triangle records
-    ext_rays = agg["eray"] + agg["pray"]
+    ext_rays = agg["eray"] + agg["pray"] - agg["tail_eray"]  # closest-hit rays traced by k_trace launches (the tail launch traces its own)
     ext_ms = agg["ext"]
     l2_peak = measure_l2_bandwidth(torch)
     achieved = ext_rays * bytes_per_ray / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
@@ -267,15 +268,15 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     px = W * H
     filt_ms = (agg["rep"] + agg["jbf"]) / args.steps
-    roofline = {"kernel": "k_extend (closest-hit traversal, 8-wide quantised BVH)", "bound": "l2", "achieved": round(achieved, 1), "peak": round(l2_peak, 1), "unit": "GB/s",
+    roofline = {"kernel": "k_trace<closest hit> (extend: traversal of the 8-wide quantised two-level BVH)", "bound": "l2", "achieved": round(achieved, 1), "peak": round(l2_peak, 1), "unit": "GB/s",
                 "frac": round(achieved / l2_peak, 4) if l2_peak else None, "traffic": None,
                 "model": {"bytes_per_ray": round(bytes_per_ray, 1), "node_visits_per_ray": round(nodes_per_ray, 2), "tri_tests_per_ray": round(tris_per_ray, 2),
-                          "rays_per_launch_avg": round(ext_rays / max(agg["waves"], 1), 0), "ms_per_step": round(ext_ms / args.steps, 4),
+                          "rays_per_launch_avg": round(ext_rays / max(agg["ext_launches"], 1), 0), "launches_per_step": round(agg["ext_launches"] / args.steps, 1), "ms_per_step": round(ext_ms / args.steps, 4),
                           "Grays_per_s_in_kernel": round(ext_rays / (ext_ms * 1e-3) / 1e9, 4) if ext_ms > 0 else None},
                 "peak_source": "measured in this run: torch.sum over an L2-resident 48 MB buffer"}
-    roofline_filters = {"kernel": "k_reproject + k_denoise_jbf", "bound": "hbm", "achieved": round((96 + 40) * px / (filt_ms * 1e-3) / 1e9, 1) if filt_ms > 0 else None,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": round((96 + 40) * px / (filt_ms * 1e-3) / 1e9 / hbm_peak, 4) if filt_ms > 0 else None,
-                        "bytes_per_pixel": {"reproject": 96, "denoise": 40}, "ms_per_step": round(filt_ms, 4),
+    roofline_filters = {"kernel": "k_reproject + k_denoise_jbf", "bound": "hbm", "achieved": round((96 + 48) * px / (filt_ms * 1e-3) / 1e9, 1) if filt_ms > 0 else None,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": round((96 + 48) * px / (filt_ms * 1e-3) / 1e9 / hbm_peak, 4) if filt_ms > 0 else None,
+                        "bytes_per_pixel": {"reproject": 96, "denoise": 48, "source": "SURVEY.md 8(d)"}, "ms_per_step": round(filt_ms, 4),
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
 
     # ---- CPU baseline: the reference's tinybvh on the rays the GPU traced (bounded sample)
@@ -296,7 +297,8 @@ def main():
         "rays_per_step": round(total_rays / args.steps, 0), "gpu_launches": total_launches,
         "e2e": {"value": round(total_rays_e2e / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "api": "CudaPathTracingRenderer::BeforeNextFrame + Render (host mirror of LogicRendererBase) + gk_readback(rtDenoised) to pinned memory"},
-        "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "shade", "acc", "rep", "jbf", "bvh")},
+        "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "shade", "tail", "acc", "rep", "jbf", "bvh")},
+        "tail_paths_per_step": round(agg["tail_paths"] / args.steps, 0),
         "host_gap_ms_per_step": round((wall_ms - dev_ms) / args.steps, 4),
         "bvh": {"blas_build_ms": round(info.msBlasBuild, 3), "tlas_build_ms": round(info.msTlasBuild, 3), "tlas_refit_ms": round(info.msRefit, 3),
                 "wide_nodes_blas": int(info.blasNodes8), "wide_nodes_tlas": int(info.tlasNodes8), "bytes": int(info.bytesBvh + info.bytesGeometry)},

@@ -114,7 +114,8 @@ class GkFrameStats(C.Structure):
                 ("launches", C.c_uint32), ("msTotal", C.c_float), ("msBvh", C.c_float), ("msGenerate", C.c_float), ("msExtend", C.c_float),
                 ("msShade", C.c_float), ("msShadow", C.c_float), ("msAccumulate", C.c_float), ("msReproject", C.c_float),
                 ("msDenoise", C.c_float), ("nodeVisits", C.c_uint64), ("triTests", C.c_uint64),
-                ("tlasVisits", C.c_uint64), ("instanceEntries", C.c_uint64), ("msTail", C.c_float), ("tailPaths", C.c_uint32)]
+                ("tlasVisits", C.c_uint64), ("instanceEntries", C.c_uint64), ("msTail", C.c_float), ("tailPaths", C.c_uint32),
+                ("tailExtensionRays", C.c_uint64), ("tailShadowRays", C.c_uint64)]
 
 
 class GkBvhInfo(C.Structure):

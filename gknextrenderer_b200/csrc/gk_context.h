@@ -158,6 +158,7 @@ struct Context {
     cudaEvent_t evA = nullptr, evB = nullptr;
     std::vector<cudaEvent_t> evPool;
     int captureWave = -1;
+    int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
     bool sahCollapse = true;        // cost-driven wide collapse (false: greedy by surface area)
     DevBuf<float4> dCapture;
     uint32_t capturedCount = 0;

@@ -288,15 +288,23 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
             enum Phase { PH_START_SAMPLE, PH_SETUP_BOUNCE, PH_POST_NEE, PH_END_SAMPLE, PH_AFTER_SAMPLES, PH_FINAL, PH_EXIT };
             Phase phase = PH_EXIT;
 
-            auto loadPrimary = [&]() {
+            // primary vertex and accumulators are fetched only by the steps that use them (sample
+            // boundaries); a bounce in the middle of a sample touches neither
+            bool havePrimary = false, haveAcc = false;
+            float accW = 0.f; // .w of both accumulators: length of the depth-of-field pixel offset
+            auto needPrimary = [&]() {
+                if (havePrimary) return;
                 const float4 a = S.primPosMat[path], b = S.primNrm[path];
                 ppos = mk3(a.x, a.y, a.z), pmat = __float_as_uint(a.w);
                 pnrm = mk3(b.x, b.y, b.z), offLen = b.w;
+                havePrimary = true;
             };
-            auto loadAcc = [&]() {
-                const float4 a = S.accDiffuse[path], b = S.accSpec[path];
-                accD = mk3(a.x, a.y, a.z), accS = mk3(b.x, b.y, b.z);
+            auto needAcc = [&]() {
                 accDirty = true;
+                if (haveAcc) return;
+                const float4 a = S.accDiffuse[path], b = S.accSpec[path];
+                accD = mk3(a.x, a.y, a.z), accS = mk3(b.x, b.y, b.z), accW = a.w;
+                haveAcc = true;
             };
             auto loadCurrent = [&]() {
                 const float4 a = S.posMat[path], c = S.dirT[path], t = S.throughput[path];
@@ -427,7 +435,7 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                     S.primNrm[path] = make_float4(pnrm.x, pnrm.y, pnrm.z, offLen);
                     bits = (mat.MaterialModel == GK_MAT_DIELECTRIC) ? F_PRIM_DIELECTRIC : 0u;
                     sample = 0;
-                    accDirty = true;
+                    accDirty = true, haveAcc = true, havePrimary = true, accW = offLen;
                     if (mat.MaterialModel == GK_MAT_DIFFUSE_LIGHT) { // Shading.slang:1003-1008
                         accD = mk3(mat.Diffuse[0], mat.Diffuse[1], mat.Diffuse[2]), accS = mk3(0, 0, 0);
                         finished = true;
@@ -438,8 +446,6 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                 }
             } else if (state == ST_BOUNCE) {
                 // ---- second half of GetRayColor (Shading.slang:965-995)
-                loadPrimary();
-                loadAcc();
                 loadCurrent();
                 const float4 hr = src.hitTuvp();
                 const uint32_t hinst = src.hitInst();
@@ -475,8 +481,6 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                     } else phase = PH_POST_NEE;
                 }
             } else if (state == ST_NEE) {
-                loadPrimary();
-                loadAcc();
                 loadCurrent();
                 const bool occluded = src.occluded();
                 if (!occluded) {
@@ -484,8 +488,6 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                     phase = PH_END_SAMPLE;
                 } else phase = PH_POST_NEE;
             } else if (state == ST_DIRECT) {
-                loadPrimary();
-                loadAcc();
                 shadowTerm = src.occluded() ? 0.f : 1.f;
                 phase = PH_FINAL;
             }
@@ -495,6 +497,7 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                 const uint32_t maxBounces = (bits & F_PRIM_DIELECTRIC) ? U.MaxNumberOfBounces : U.NumberOfBounces;
                 switch (phase) {
                 case PH_START_SAMPLE:
+                    needPrimary();
                     color = mk3(1, 1, 1);
                     dir = normalize3(ppos - eye);
                     vpos = ppos, vnrm = pnrm, vmat = pmat;
@@ -519,7 +522,9 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                     break;
                 }
                 case PH_END_SAMPLE: {
+                    needAcc();
                     if (bits & F_HIT_METAL) {
+                        needPrimary();
                         const GkMaterial& pm = SS.materials[pmat];
                         color = color * mk3(pm.Diffuse[0], pm.Diffuse[1], pm.Diffuse[2]);
                     }
@@ -530,9 +535,11 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                     break;
                 }
                 case PH_AFTER_SAMPLES: {
+                    needAcc();
                     accD = accD / float(samples);
                     accS = accS / float(samples);
                     if (U.HasSun) { // DirectIlluminate, Shading.slang:826-845
+                        needPrimary();
                         const f3 lv = mk3(U.SunDirection[0], U.SunDirection[1], U.SunDirection[2]);
                         const f3 cone = alignWithNormal(randomInCone(rng, cosf(0.25f / 180.f * kPi)), lv);
                         e.kind = 2, e.o = ppos, e.d = cone, e.tmin = kEps, e.tmax = kMaxTrace;
@@ -546,6 +553,8 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                 }
                 case PH_FINAL: {
                     if (!finished) {
+                        needPrimary();
+                        needAcc();
                         const f3 lv = mk3(U.SunDirection[0], U.SunDirection[1], U.SunDirection[2]);
                         const float d = fmaxx(dot3(lv, normalize3(pnrm)), 0.0f) * kInvPi;
                         accD = accD + mk3(U.SunColor[0], U.SunColor[1], U.SunColor[2]) * d * shadowTerm;
@@ -567,8 +576,8 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                 S.throughput[path] = make_float4(color.x, color.y, color.z, 0);
             }
             if (accDirty) {
-                S.accDiffuse[path] = make_float4(accD.x, accD.y, accD.z, offLen);
-                S.accSpec[path] = make_float4(accS.x, accS.y, accS.z, offLen);
+                S.accDiffuse[path] = make_float4(accD.x, accD.y, accD.z, accW);
+                S.accSpec[path] = make_float4(accS.x, accS.y, accS.z, accW);
             }
             S.nrmFlags[path] = make_float4(vnrm.x, vnrm.y, vnrm.z, __uint_as_float(packFlags(state, bits, bounce, sample)));
         }
@@ -599,7 +608,8 @@ __device__ __forceinline__ void appendRay(const Emit& e, uint32_t path, const Ra
     }
 }
 
-__global__ void __launch_bounds__(256) k_shade(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, ShadeScene SS, PathState S, PlaneView PL, RayQueue inE,
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_shade(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, ShadeScene SS, PathState S, PlaneView PL, RayQueue inE,
                                                uint32_t countE, RayQueue inS, uint32_t countS, RayQueue outE, RayQueue outS)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -862,6 +872,7 @@ GkStatus traceFrame(Context& c)
     uint32_t countE = n, countS = 0;
     bool tailRan = false;
     fs.tailPaths = 0;
+    fs.tailExtensionRays = fs.tailShadowRays = 0;
     fs.primaryRays = (uint64_t)c.ownedRows * c.width;
     c.capturedCount = 0;
     for (uint32_t wave = 0; wave < 4096; ++wave) {
@@ -901,8 +912,12 @@ GkStatus traceFrame(Context& c)
         const int nxt = cur ^ 1;
         GK_CUDA(cudaMemsetAsync(c.extendQ[nxt].count, 0, sizeof(uint32_t), st));
         GK_CUDA(cudaMemsetAsync(c.shadowQ[nxt].count, 0, sizeof(uint32_t), st));
-        k_shade<<<gridFor((size_t)countE + countS), 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.extendQ[nxt],
-                                                              c.shadowQ[nxt]);
+        if (c.shadeMinBlocks >= 3)
+            k_shade<3><<<gridFor((size_t)countE + countS), 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.extendQ[nxt],
+                                                                     c.shadowQ[nxt]);
+        else
+            k_shade<2><<<gridFor((size_t)countE + countS), 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.extendQ[nxt],
+                                                                     c.shadowQ[nxt]);
         fs.launches++;
         const size_t f = mark();
         spans.push_back({a, b, 1}), spans.push_back({b, d, 2}), spans.push_back({d, f, 3});
@@ -937,6 +952,7 @@ GkStatus traceFrame(Context& c)
         unsigned long long t[2];
         memcpy(t, c.hCounts + 2, sizeof(t));
         fs.extensionRays += t[0], fs.shadowRays += t[1];
+        fs.tailExtensionRays = t[0], fs.tailShadowRays = t[1];
     }
     if (c.travStats) {
         TraversalStats h;

@@ -96,6 +96,7 @@ typedef struct GkFrameStats {
     uint64_t tlasVisits, instanceEntries; /* ditto: node visits in the TLAS, ray -> instance transitions */
     float msTail;       /* the single launch that finishes the last paths of the frame */
     uint32_t tailPaths; /* paths alive when that launch started */
+    uint64_t tailExtensionRays, tailShadowRays; /* part of extensionRays / shadowRays traced by that launch */
 } GkFrameStats;
 
 typedef struct GkBvhInfo {
