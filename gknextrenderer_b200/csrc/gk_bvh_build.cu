@@ -495,7 +495,8 @@ __global__ void k_quantise(Bvh2View B, WideNode* __restrict__ nodes, const uint3
         if (i < (int)n.count && lo[i].x <= hi[i].x) {
             const float l3[3] = {lo[i].x, lo[i].y, lo[i].z}, h3[3] = {hi[i].x, hi[i].y, hi[i].z};
             for (int a = 0; a < 3; ++a) {
-                // >= 1/64 step of slack on both sides: the traversal's decode error is far below it
+                // one whole quantisation step of slack on both sides: covers the decode error of the
+                // traversal (MUFU reciprocal, fused t = q*s + b) with a wide margin
                 const float ql = floorf((l3[a] - org[a]) / step[a] - 1.0f), qh = ceilf((h3[a] - org[a]) / step[a] + 1.0f);
                 n.c[i].qlo[a] = (uint8_t)fminf(fmaxf(ql, 0.f), 255.f);
                 n.c[i].qhi[a] = (uint8_t)fminf(fmaxf(qh, 0.f), 255.f);

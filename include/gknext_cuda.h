@@ -51,8 +51,7 @@ typedef struct GkConfig {
 } GkConfig;
 
 enum GkConfigFlags {
-    GK_CFG_DEFAULT = 0,
-    GK_CFG_BVH2_TRAVERSAL = 1u << 0 /* debug: traverse the binary LBVH instead of the 8-wide nodes */
+    GK_CFG_DEFAULT = 0
 };
 
 /* Image planes, named after the reference's render targets
