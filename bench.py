@@ -300,7 +300,7 @@ def main():
         "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "shade", "tail", "acc", "rep", "jbf", "bvh")},
         "tail_paths_per_step": round(agg["tail_paths"] / args.steps, 0),
         "host_gap_ms_per_step": round((wall_ms - dev_ms) / args.steps, 4),
-        "bvh": {"blas_build_ms": round(info.msBlasBuild, 3), "tlas_build_ms": round(info.msTlasBuild, 3), "tlas_refit_ms": round(info.msRefit, 3),
+        "bvh": {"blas_build_ms": round(info.msBlasBuild, 3), "tlas_build_ms": round(info.msTlasBuild, 3), "tlas_refit_ms": round(info.msRefit, 3), "refits_rejected": int(r.bvh_info().refitsRejected),
                 "wide_nodes_blas": int(info.blasNodes8), "wide_nodes_tlas": int(info.tlasNodes8), "bytes": int(info.bytesBvh + info.bytesGeometry)},
         "roofline": roofline, "roofline_filters": roofline_filters, "cpu_baseline": cpu, "clocks": clocks,
     }

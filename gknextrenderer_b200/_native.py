@@ -122,7 +122,7 @@ class GkBvhInfo(C.Structure):
     _fields_ = [("blasCount", C.c_uint32), ("instanceCount", C.c_uint32), ("triangleCount", C.c_uint64), ("instancedTriangles", C.c_uint64),
                 ("blasNodes2", C.c_uint32), ("blasNodes8", C.c_uint32), ("tlasNodes2", C.c_uint32), ("tlasNodes8", C.c_uint32),
                 ("bytesGeometry", C.c_uint64), ("bytesBvh", C.c_uint64), ("msBlasBuild", C.c_float), ("msTlasBuild", C.c_float),
-                ("msRefit", C.c_float)]
+                ("msRefit", C.c_float), ("refitsRejected", C.c_uint32), ("tlasAreaAtBuild", C.c_float)]
 
 
 # every symbol include/gknext_cuda.h declares: name -> (restype, argtypes)
@@ -151,6 +151,8 @@ CUDA_API = {
     "gk_exchange_bytes": (C.c_size_t, [_P]),
     "gk_exchange_pack": (C.c_int, [_P, _P]),
     "gk_exchange_unpack": (C.c_int, [_P, _P]),
+    "gk_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "gk_host_free": (None, [C.c_void_p]),
     "gk_synchronize": (C.c_int, [_P]),
     "gk_get_stats": (C.c_int, [_P, C.POINTER(GkFrameStats)]),
     "gk_get_bvh_info": (C.c_int, [_P, C.POINTER(GkBvhInfo)]),

@@ -154,7 +154,7 @@ void gk_destroy(GkContext* ctx)
     c.blasTree.release(), c.tlasTree.release();
     c.dModels.release(), c.dGpuVerts.release(), c.dIndices.release(), c.dMaterials.release(), c.dLights.release(), c.dFaceNormals.release();
     c.dNodes.release(), c.dCubes.release(), c.dVoxels.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dBlasSrc.release(), c.dTlasSrc.release(), c.dInst.release();
-    c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release();
+    c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release(), c.dRootRef.release();
     c.dCapture.release();
     for (cudaEvent_t e : c.evPool) cudaEventDestroy(e);
     if (c.stream) cudaStreamDestroy(c.stream);
@@ -383,6 +383,21 @@ GkStatus gk_exchange_unpack(GkContext* ctx, const void* d_all)
     return exchangeUnpack(c, d_all);
 }
 
+void* gk_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void gk_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 GkStatus gk_synchronize(GkContext* ctx)
 {
     GK_CHECK_CTX(ctx);
@@ -420,6 +435,7 @@ GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out)
     out->bytesGeometry = c.totalTris * sizeof(TriRecord) + c.dGpuVerts.bytes() + c.dIndices.bytes();
     out->bytesBvh = (uint64_t)(c.blasNodeCount + c.tlasNodeCount) * sizeof(WideNode) + (uint64_t)c.nodeCount * sizeof(InstRecord);
     out->msBlasBuild = c.msBlasBuild, out->msTlasBuild = c.msTlasBuild, out->msRefit = c.msRefit;
+    out->refitsRejected = c.refitRejected, out->tlasAreaAtBuild = c.tlasAreaAtBuild;
     return GK_OK;
 }
 

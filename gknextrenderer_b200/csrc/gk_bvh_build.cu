@@ -163,6 +163,7 @@ __global__ void k_leaf_boxes(const float4* __restrict__ plo, const float4* __res
 // Cost model of the wide collapse (node visit = 1): one triangle test, one instance entry.
 constexpr float kCostTri = 0.3f;
 constexpr float kCostInstance = 1.5f;
+constexpr float kRefitGrowthLimit = 1.25f;
 
 __device__ __forceinline__ float boxAreaOrZero(float lx, float ly, float lz, float hx, float hy, float hz)
 {
@@ -177,14 +178,16 @@ __device__ __forceinline__ float boxAreaOrZero(float lx, float ly, float lz, flo
 // its parent's wide node (i = 1..7); slot [7] holds the cost of n as a wide node of its own.
 __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right, const uint32_t* __restrict__ parentI,
                                    const uint32_t* __restrict__ parentL, const float4* llo, const float4* lhi, float4* ilo, float4* ihi, int* flags,
-                                   float* cost, const uint32_t* __restrict__ first, const uint32_t* __restrict__ last, uint32_t leafMax, float primCost)
+                                   float* cost, const uint32_t* __restrict__ first, const uint32_t* __restrict__ last, uint32_t leafMax, float primCost,
+                                   float* __restrict__ areaSum)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n || n < 2) return;
     uint32_t cur = parentL[k];
+    float myArea = 0.f; // surface area of the internal nodes this thread completes (tree quality measure)
     while (cur != kInvalid) {
         __threadfence();
-        if (atomicAdd(&flags[cur], 1) == 0) return; // first arrival: the sibling subtree finishes the job
+        if (atomicAdd(&flags[cur], 1) == 0) break; // first arrival: the sibling subtree finishes the job
         const uint32_t L = left[cur], R = right[cur];
         const volatile float4* pl0 = (L & kLeafBit) ? llo + (L & 0x7fffffffu) : ilo + L;
         const volatile float4* ph0 = (L & kLeafBit) ? lhi + (L & 0x7fffffffu) : ihi + L;
@@ -195,6 +198,7 @@ __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left
         const float lx = fminf(l0x, l1x), ly = fminf(l0y, l1y), lz = fminf(l0z, l1z);
         const float hx = fmaxf(h0x, h1x), hy = fmaxf(h0y, h1y), hz = fmaxf(h0z, h1z);
         ilo[cur] = make_float4(lx, ly, lz, 0), ihi[cur] = make_float4(hx, hy, hz, 0);
+        myArea += boxAreaOrZero(lx, ly, lz, hx, hy, hz);
         if (cost) {
             float cl[7], cr[7];
             if (L & kLeafBit) {
@@ -239,6 +243,7 @@ __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left
         }
         cur = parentI[cur];
     }
+    if (areaSum && myArea > 0.f) atomicAdd(areaSum, myArea);
 }
 
 // ------------------------------------------------------------------ per-group roots
@@ -632,7 +637,7 @@ static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint3
     return GK_OK;
 }
 
-static GkStatus propagateBounds(Context& c, Lbvh& T, bool withCost, uint32_t leafMax, float primCost)
+static GkStatus propagateBounds(Context& c, Lbvh& T, bool withCost, uint32_t leafMax, float primCost, float* dAreaSum = nullptr)
 {
     const uint32_t n = T.n;
     cudaStream_t st = c.stream;
@@ -642,7 +647,7 @@ static GkStatus propagateBounds(Context& c, Lbvh& T, bool withCost, uint32_t lea
         if (withCost) GK_CUDA(T.cost.reserve(8 * (size_t)n));
         GK_CUDA(cudaMemsetAsync(T.flags.p, 0, sizeof(int) * n, st));
         k_propagate_bounds<<<gridFor(n), 256, 0, st>>>(n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, T.llo.p, T.lhi.p, T.ilo.p, T.ihi.p, T.flags.p,
-                                                       withCost ? T.cost.p : nullptr, T.first.p, T.last.p, leafMax, primCost);
+                                                       withCost ? T.cost.p : nullptr, T.first.p, T.last.p, leafMax, primCost, dAreaSum);
         T.costValid = withCost;
         T.primCost = primCost;
     }
@@ -758,22 +763,38 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
     GK_CUDA(c.dInst.reserve(count));
     k_update_instances<<<gridFor(count, 128), 128, 0, st>>>(c.dNodes.p, count, c.dModels.p, (uint32_t)c.models.size(), c.dInst.p, T.plo.p, T.phi.p);
     GkStatus s;
+    GK_CUDA(c.dCounters.reserve(8));
+    float* dArea = reinterpret_cast<float*>(c.dCounters.p + 4);
+    float area = 0.f;
+    if (refit) {
+        // Refit = new boxes on the old topology.  It is kept only while the tree stays good: the summed
+        // surface area of the internal nodes may grow to kRefitGrowthLimit x its value at the last build
+        // (instances that jump across the scene inflate every ancestor; then a rebuild is cheaper than
+        // tracing through the bloated tree).
+        GK_CUDA(cudaMemsetAsync(dArea, 0, sizeof(float), st));
+        s = propagateBounds(c, T, false, 0, kCostInstance, dArea);
+        if (s != GK_OK) return s;
+        GK_CUDA(cudaMemcpyAsync(&area, dArea, sizeof(float), cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        if (area <= kRefitGrowthLimit * c.tlasAreaAtBuild) {
+            if (c.tlasNodeCount) k_quantise<<<gridFor(c.tlasNodeCount, 128), 128, 0, st>>>(viewOf(T), c.dTlasNodes.p, c.dTlasSrc.p, c.tlasNodeCount);
+        } else {
+            refit = false;
+            c.refitRejected++;
+        }
+    }
     if (!refit) {
         s = buildRadixTree(c, T, nullptr, 1, 42);
         if (s != GK_OK) return s;
-    }
-    s = propagateBounds(c, T, c.sahCollapse && !refit, 0, kCostInstance);
-    if (s != GK_OK) return s;
-    if (!refit) {
-        DevBuf<uint32_t> rootRef;
-        GK_CUDA(rootRef.reserve(1));
-        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.dTlasSrc, c.tlasNodeCount, rootRef.p);
+        GK_CUDA(cudaMemsetAsync(dArea, 0, sizeof(float), st));
+        s = propagateBounds(c, T, c.sahCollapse, 0, kCostInstance, dArea);
         if (s != GK_OK) return s;
-        GK_CUDA(cudaMemcpyAsync(&c.tlasRoot, rootRef.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaMemcpyAsync(&c.tlasAreaAtBuild, dArea, sizeof(float), cudaMemcpyDeviceToHost, st));
+        GK_CUDA(c.dRootRef.reserve(1));
+        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.dTlasSrc, c.tlasNodeCount, c.dRootRef.p);
+        if (s != GK_OK) return s;
+        GK_CUDA(cudaMemcpyAsync(&c.tlasRoot, c.dRootRef.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaStreamSynchronize(st));
-        rootRef.release();
-    } else if (c.tlasNodeCount) {
-        k_quantise<<<gridFor(c.tlasNodeCount, 128), 128, 0, st>>>(viewOf(T), c.dTlasNodes.p, c.dTlasSrc.p, c.tlasNodeCount);
     }
     cudaEventRecord(e1, st);
     GK_CUDA(cudaGetLastError());

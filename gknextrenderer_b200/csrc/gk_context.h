@@ -158,6 +158,9 @@ struct Context {
     cudaEvent_t evA = nullptr, evB = nullptr;
     std::vector<cudaEvent_t> evPool;
     int captureWave = -1;
+    float tlasAreaAtBuild = 0.f;    // summed internal-node area of the TLAS when it was last built
+    uint32_t refitRejected = 0;     // refits that degraded the tree too much and became rebuilds
+    DevBuf<uint32_t> dRootRef;
     int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
     bool sahCollapse = true;        // cost-driven wide collapse (false: greedy by surface area)
     DevBuf<float4> dCapture;

@@ -1,7 +1,12 @@
 // gk_assets.cpp — see gk_assets.h.
 #include "gk_assets.h"
+#include "../../include/gknext_cuda.h"
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
+#include <new>
 #include <random>
+#include <unordered_set>
 
 namespace gk::Assets {
 
@@ -200,7 +205,16 @@ void Node::RecalcTransform(bool) { RecalcLocalTransform(); transform_ = localTra
 
 bool Node::TickVelocity(mat4& combinedTS) // Model.cpp:1279-1296
 {
-    combinedTS = prevTransform_ * inverse(transform_);
+    // same arithmetic as the reference every time it is evaluated; a node at rest (prev == cur, both
+    // unchanged since the last tick) re-uses the matrix it produced then
+    const bool atRest = !(prevTransform_ != transform_);
+    if (atRest && steadyValid_) {
+        combinedTS = steadyCombined_;
+    } else {
+        combinedTS = prevTransform_ * inverse(transform_);
+        steadyValid_ = atRest;
+        if (atRest) steadyCombined_ = combinedTS;
+    }
     prevTransform_ = transform_;
     vec4 p = combinedTS * vec4(0, 0, 0, 1);
     return (p.x * p.x + p.y * p.y + p.z * p.z) > 0.1f;
@@ -210,6 +224,32 @@ void Node::SetMaterial(const std::vector<uint32_t>& m)
 {
     materialIdx_.fill(0);
     for (size_t i = 0; i < m.size() && i < 16; ++i) materialIdx_[i] = m[i];
+}
+
+static std::mutex gProxyMutex;
+static std::unordered_set<void*> gPinned;
+
+void* ProxyAlloc(size_t bytes)
+{
+    if (void* p = gk_host_alloc(bytes)) {
+        std::lock_guard<std::mutex> lock(gProxyMutex);
+        gPinned.insert(p);
+        return p;
+    }
+    void* p = malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+
+void ProxyFree(void* p)
+{
+    bool pinned;
+    {
+        std::lock_guard<std::mutex> lock(gProxyMutex);
+        pinned = gPinned.erase(p) != 0;
+    }
+    if (pinned) gk_host_free(p);
+    else free(p);
 }
 
 NodeProxy Node::GetNodeProxy() const // Model.cpp:1326-1342
@@ -235,11 +275,11 @@ bool Scene::UpdateNodes() // Scene.cpp:464-511
         if (node->GetModel() >= models_.size()) continue;
         const Model& model = models_[node->GetModel()];
         for (uint32_t section = 0; section < model.SectionCount(); ++section) {
-            NodeProxy proxy = node->GetNodeProxy();
+            nodeProxys_.push_back(node->GetNodeProxy());
+            NodeProxy& proxy = nodeProxys_.back();
             memcpy(proxy.combinedPrevTS, combined.data(), 64);
             proxy.modelId = node->GetModel() * 10 + section;
             proxy.nort = section == 0 ? 0 : 1;
-            nodeProxys_.push_back(proxy);
         }
     }
     return true;

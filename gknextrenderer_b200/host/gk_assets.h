@@ -131,10 +131,27 @@ private:
     quat rotation_;
     vec3 scaling_;
     mat4 localTransform_, transform_, prevTransform_;
+    mat4 steadyCombined_;        // prev * inverse(cur) of a node at rest, kept while the transform is unchanged
+    bool steadyValid_ = false;
     uint32_t modelId_, instanceId_;
     bool visible_ = true;
     std::array<uint32_t, 16> materialIdx_{};
 };
+
+// Storage of the per-frame node proxies: page-locked when a CUDA device is present (the reference
+// writes them into a mapped device buffer, Scene.cpp:464-511), ordinary memory otherwise.
+void* ProxyAlloc(size_t bytes);
+void ProxyFree(void* p);
+template <class T> struct ProxyAllocator {
+    using value_type = T;
+    ProxyAllocator() = default;
+    template <class U> ProxyAllocator(const ProxyAllocator<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(ProxyAlloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t) { ProxyFree(p); }
+    template <class U> bool operator==(const ProxyAllocator<U>&) const { return true; }
+    template <class U> bool operator!=(const ProxyAllocator<U>&) const { return false; }
+};
+using ProxyVector = std::vector<NodeProxy, ProxyAllocator<NodeProxy>>;
 
 class Scene {
 public:
@@ -149,7 +166,7 @@ public:
     void SetSelectedId(uint32_t id) { selectedId_ = id; }
     // Scene::UpdateNodesGpuDriven (Scene.cpp:464-511): one proxy per (drawable node, section).
     bool UpdateNodes();
-    const std::vector<NodeProxy>& GetNodeProxys() const { return nodeProxys_; }
+    const ProxyVector& GetNodeProxys() const { return nodeProxys_; }
     void MarkDirty() { sceneDirty_ = true; }
     std::vector<GkMaterial> GpuMaterials() const;
 
@@ -164,7 +181,7 @@ private:
     EnvironmentSetting envSettings_;
     uint32_t cameraIdx_ = 0, selectedId_ = (uint32_t)-1;
     bool sceneDirty_ = true;
-    std::vector<NodeProxy> nodeProxys_;
+    ProxyVector nodeProxys_;
     std::vector<GkModelDesc> modelDescs_;
     std::vector<GkMaterial> gpuMaterials_;
     GkSceneDesc desc_{};

@@ -142,9 +142,9 @@ void CudaPathTracingRenderer::BeforeNextFrame()
     if (scene.UpdateNodes() || !instancesUploaded_) {
         const auto& px = scene.GetNodeProxys();
         // The reference rebuilds its TLAS on every dirty frame (RayTraceBaseRenderer.cpp:216-228).
-        // Here moving instances refit the existing tree and a full rebuild runs every 8th update
-        // (or when the instance count changes) to keep the tree quality bounded.
-        const bool refit = instancesUploaded_ && px.size() == lastInstanceCount_ && (updatesSinceRebuild_ % 8) != 7;
+        // Here an update with an unchanged instance count may refit the existing tree; the backend
+        // falls back to a rebuild by itself when the refitted tree got too loose.
+        const bool refit = instancesUploaded_ && px.size() == lastInstanceCount_;
         check(gk_update_instances(ctx_, px.data(), (uint32_t)px.size(), refit ? 1 : 0), "gk_update_instances");
         updatesSinceRebuild_ = refit ? updatesSinceRebuild_ + 1 : 0;
         lastInstanceCount_ = px.size();

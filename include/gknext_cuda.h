@@ -105,6 +105,8 @@ typedef struct GkBvhInfo {
     uint32_t blasNodes2, blasNodes8, tlasNodes2, tlasNodes8;
     uint64_t bytesGeometry, bytesBvh;
     float msBlasBuild, msTlasBuild, msRefit;
+    uint32_t refitsRejected; /* refits that loosened the TLAS beyond the growth limit and were rebuilt instead */
+    float tlasAreaAtBuild;   /* summed internal-node surface area of the TLAS at its last build */
 } GkBvhInfo;
 
 int gk_abi_version(void);
@@ -173,6 +175,12 @@ void* gk_plane_device(GkContext* ctx, GkPlane plane);
 size_t gk_exchange_bytes(const GkContext* ctx);
 GkStatus gk_exchange_pack(GkContext* ctx, void* d_staging);
 GkStatus gk_exchange_unpack(GkContext* ctx, const void* d_all);
+
+/* Page-locked host memory for arrays that are uploaded every frame (the node proxies: the reference
+ * writes them straight into a mapped device buffer, src/Assets/Scene.cpp:464-511).  Returns NULL when
+ * no CUDA device is usable; the caller then keeps using ordinary memory. */
+void* gk_host_alloc(size_t bytes);
+void gk_host_free(void* p);
 
 GkStatus gk_synchronize(GkContext* ctx);
 GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out);

@@ -269,7 +269,38 @@ def test_refit_equals_rebuild_after_moving_instances(built):
         r.update_instances(nodes, n, refit=True)
         orc.set_nodes(nodes, n)
         _compare_hits(r, orc, rays, f"bricks refit f{frame}")
-    assert r.bvh_info().msRefit > 0
+    info = r.bvh_info()
+    assert info.msRefit > 0 or info.refitsRejected > 0  # refitted, or judged too loose and rebuilt
+
+
+def test_small_motion_refits_and_teleports_fall_back_to_rebuild(built):
+    """gk_update_instances(refit=1) keeps the topology only while the summed node area stays within the
+    growth limit; bricks that jump across the field must trigger a rebuild (and stay bit-exact)."""
+    eng, r, orc, (nodes, n) = _setup("bricks", 64, 64, (3000, 42))
+    rng = np.random.default_rng(11)
+    rays = _random_rays(rng, 50000, (-20, 0.0, -20), (20, 3.0, 20))
+    rays[:, 5] = -np.abs(rays[:, 5]) - 0.2
+    # one lattice cell sideways for 20 bricks: a refit must be accepted
+    for i in range(1, 21):
+        t = nodes[i].worldTS
+        eng.set_node_translation(i, t[12] + 0.08, t[13], t[14])
+    eng.mark_dirty()
+    nodes, n = eng.update_nodes()
+    r.update_instances(nodes, n, refit=True)
+    orc.set_nodes(nodes, n)
+    info = r.bvh_info()
+    assert info.refitsRejected == 0 and info.msRefit > 0
+    _compare_hits(r, orc, rays, "bricks nudged (refit)")
+    # 1 % of the bricks teleport per step: within a few steps the refitted tree is too loose
+    for frame in range(1, 13):
+        eng.step_scene(frame)
+        nodes, n = eng.update_nodes()
+        r.update_instances(nodes, n, refit=True)
+        if r.bvh_info().refitsRejected > 0:
+            break
+    assert r.bvh_info().refitsRejected > 0
+    orc.set_nodes(nodes, n)
+    _compare_hits(r, orc, rays, "bricks teleported (rebuilt)")
 
 
 # ---------------------------------------------------------------- filters
