@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(TX* TY) k_reproject(const GkUniformBufferObjec
     __shared__ uint2 sSrc[3][RHT][RW];
     __shared__ uint2 sNrm[RHT][RW];
     __shared__ uint32_t sId[RHT][RW];
+    __shared__ float4 sYc[RHT][RW]; // YCoCg of the albedo texels: each is read by 25 neighbours for the clamp box
     const GkUniformBufferObject& U = *ubo;
     const int W = A.W, H = A.H;
     const int vx = (int)U.ViewportRect[0], vy = (int)U.ViewportRect[1];
@@ -107,7 +108,10 @@ __global__ void __launch_bounds__(TX* TY) k_reproject(const GkUniformBufferObjec
             const int gx = bx + lx - RH, gy = by + ly - RH;
             sSrc[0][ly][lx] = loadPx(A.src[0], gx, gy, W, H);
             sSrc[1][ly][lx] = loadPx(A.src[1], gx, gy, W, H);
-            sSrc[2][ly][lx] = loadPx(A.src[2], gx, gy, W, H);
+            const uint2 alb = loadPx(A.src[2], gx, gy, W, H);
+            sSrc[2][ly][lx] = alb;
+            const c3 yc = rgb2ycocg(unpackRgb(alb));
+            sYc[ly][lx] = make_float4(yc.x, yc.y, yc.z, 0.f);
             sNrm[ly][lx] = loadPx(A.normal, gx, gy, W, H);
             sId[ly][lx] = loadId(A.id0, gx, gy, W, H);
         }
@@ -138,25 +142,29 @@ __global__ void __launch_bounds__(TX* TY) k_reproject(const GkUniformBufferObjec
         for (int ch = 0; ch < 3; ++ch) A.out[ch][pi] = packRgba(unpackRgb(sSrc[ch][ly][lx]), 1.0f);
         return;
     }
-    // spatial fallback weights are shared by the three channel sets (ReProject:93-121)
-    const int R = U.DisableSpatialReuse ? 0 : 2;
-    const c3 cn = unpackRgb(sNrm[ly][lx]);
-    float w[25];
-    float total = 0.f;
-#pragma unroll
-    for (int dy = -2; dy <= 2; ++dy)
-#pragma unroll
-        for (int dx = -2; dx <= 2; ++dx) {
-            float wt = 0.f;
-            if (dx >= -R && dx <= R && dy >= -R && dy <= R) {
-                const float cd = sqrtf(float(dx) * float(dx) + float(dy) * float(dy));
-                wt = calculateWeight(cd, sId[ly + dy][lx + dx] == cur0, dx == 0 && dy == 0, unpackRgb(sNrm[ly + dy][lx + dx]), cn);
-                total += wt;
-            }
-            w[(dy + 2) * 5 + dx + 2] = wt;
-        }
     uint32_t p0 = loadId(A.id1, px, py, W, H), p1 = loadId(A.id1, px + 1, py, W, H), p2 = loadId(A.id1, px, py + 1, W, H), p3 = loadId(A.id1, px + 1, py + 1, W, H);
     if (sqrtf(motion.x * motion.x + motion.y * motion.y) < 0.02f) p0 = p1 = p2 = p3 = cur0;
+    // The 5x5 spatial estimate only replaces history taps whose object id differs (ReProject:139-147):
+    // where all four taps are accepted it is never read, so it is not computed.
+    const bool needSpatial = !(cur0 == p0 && cur0 == p1 && cur0 == p2 && cur0 == p3);
+    const int R = U.DisableSpatialReuse ? 0 : 2;
+    float w[25];
+    float total = 0.f;
+    if (needSpatial) { // weights are shared by the three channel sets (ReProject:93-121)
+        const c3 cn = unpackRgb(sNrm[ly][lx]);
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                float wt = 0.f;
+                if (dx >= -R && dx <= R && dy >= -R && dy <= R) {
+                    const float cd = sqrtf(float(dx) * float(dx) + float(dy) * float(dy));
+                    wt = calculateWeight(cd, sId[ly + dy][lx + dx] == cur0, dx == 0 && dy == 0, unpackRgb(sNrm[ly + dy][lx + dx]), cn);
+                    total += wt;
+                }
+                w[(dy + 2) * 5 + dx + 2] = wt;
+            }
+    }
     const float sx = fxp - floorf(fxp), sy = fyp - floorf(fyp);
     const uint32_t tf = U.TemporalFrames > 1 ? U.TemporalFrames : 1;
     const float keep = clampx(1.0f / float(tf), 0.0f, 1.0f);
@@ -166,19 +174,25 @@ __global__ void __launch_bounds__(TX* TY) k_reproject(const GkUniformBufferObjec
         c3 spatial = mk(0, 0, 0);
         c3 mn = mk(0, 0, 0), mx = mk(0, 0, 0);
         const c3 src = unpackRgb(sSrc[ch][ly][lx]);
-        if (needClamp) mn = mx = rgb2ycocg(src);
+        if (needSpatial) {
 #pragma unroll
-        for (int dy = -2; dy <= 2; ++dy)
+            for (int dy = -2; dy <= 2; ++dy)
 #pragma unroll
-            for (int dx = -2; dx <= 2; ++dx) {
-                const c3 s = unpackRgb(sSrc[ch][ly + dy][lx + dx]);
-                if (dx >= -R && dx <= R && dy >= -R && dy <= R) spatial = spatial + s * w[(dy + 2) * 5 + dx + 2];
-                if (needClamp) {
-                    const c3 yc = rgb2ycocg(s);
+                for (int dx = -2; dx <= 2; ++dx)
+                    if (dx >= -R && dx <= R && dy >= -R && dy <= R) spatial = spatial + unpackRgb(sSrc[ch][ly + dy][lx + dx]) * w[(dy + 2) * 5 + dx + 2];
+            spatial = spatial / total;
+        }
+        if (needClamp) {
+            mn = mx = rgb2ycocg(src);
+#pragma unroll
+            for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const float4 t = sYc[ly + dy][lx + dx];
+                    const c3 yc = mk(t.x, t.y, t.z);
                     mn = min3(mn, yc), mx = max3(mx, yc);
                 }
-            }
-        spatial = spatial / total;
+        }
         const c3 h0 = cur0 == p0 ? unpackRgb(loadPx(A.hist[ch], px, py, W, H)) : spatial;
         const c3 h1 = cur0 == p1 ? unpackRgb(loadPx(A.hist[ch], px + 1, py, W, H)) : spatial;
         const c3 h2 = cur0 == p2 ? unpackRgb(loadPx(A.hist[ch], px, py + 1, W, H)) : spatial;
@@ -254,44 +268,50 @@ constexpr int DW = TX + 2 * DH, DHT = TY + 2 * DH;
 
 __global__ void __launch_bounds__(TX* TY) k_denoise_jbf(const GkUniformBufferObject* __restrict__ ubo, DenoiseArgs A)
 {
-    __shared__ uint2 sDif[DHT][DW];
+    __shared__ float4 sDif[DHT][DW]; // diffuse + 0.001 bias (DenoiseJBF:37), w = its luminance
+    __shared__ float sFi[36];        // spatial weights of the 36 taps: they depend on the tap only
     const GkUniformBufferObject& U = *ubo;
     const int W = A.W, H = A.H;
     const int vx = (int)U.ViewportRect[0], vy = (int)U.ViewportRect[1];
     const int bx = blockIdx.x * TX + vx, by = blockIdx.y * TY + vy;
     const bool filter = U.BFSize > 0;
     if (filter) {
-        for (int i = threadIdx.y * TX + threadIdx.x; i < DW * DHT; i += TX * TY) {
+        const int t = threadIdx.y * TX + threadIdx.x;
+        for (int i = t; i < DW * DHT; i += TX * TY) {
             const int ly = i / DW, lx = i - ly * DW;
-            sDif[ly][lx] = loadPx(A.diffuse, bx + lx - DH, by + ly - DH, W, H);
+            const c3 c = unpackRgb(loadPx(A.diffuse, bx + lx - DH, by + ly - DH, W, H)) + mk(0.001f, 0.001f, 0.001f);
+            sDif[ly][lx] = make_float4(c.x, c.y, c.z, c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f);
+        }
+        if (t < 36) {
+            const int i = 2 * (t / 6) - 5, j = 2 * (t % 6) - 5;
+            const float dist = clampx(float(i * i + j * j) / float(5 * 5), 0.0f, 1.0f);
+            sFi[t] = expf(-dist * dist / (2.0f * U.BFSigma * U.BFSigma));
         }
         __syncthreads();
     }
     const int x = bx + threadIdx.x, y = by + threadIdx.y;
     if (x >= W || y >= H) return;
     const size_t pi = (size_t)y * W + x;
-    const c3 lumW = mk(0.212671f, 0.715160f, 0.072169f);
     const c3 bias = mk(0.001f, 0.001f, 0.001f);
     c3 Total = mk(0, 0, 0);
     const c3 specC = unpackRgb(__ldg(A.spec + pi)), albC = unpackRgb(__ldg(A.albedo + pi));
     if (filter) {
         const int lx = threadIdx.x + DH, ly = threadIdx.y + DH;
-        const float sigma = U.BFSigma, sigmaL = U.BFSigmaLum * 100.0f;
-        const c3 cc = unpackRgb(sDif[ly][lx]) + bias;
+        const float sigmaL = U.BFSigmaLum * 100.0f;
+        const float invL = 1.0f / (2.0f * sigmaL * sigmaL);
         const c3 cs = specC + bias;
-        const float clum = cc.x * lumW.x + cc.y * lumW.y + cc.z * lumW.z;
+        const float clum = sDif[ly][lx].w;
         float Weight = 0;
 #pragma unroll
         for (int i = -5; i <= 5; i += 2)
 #pragma unroll
             for (int j = -5; j <= 5; j += 2) {
-                const c3 Ci = unpackRgb(sDif[ly + i][lx + j]) + bias;
-                const float lumi = Ci.x * lumW.x + Ci.y * lumW.y + Ci.z * lumW.z;
-                const float dist = clampx(float(i * i + j * j) / float(5 * 5), 0.0f, 1.0f);
-                const float dl = (clum - lumi) * (clum - lumi);
-                const float Fi = expf(-dist * dist / (2.0f * sigma * sigma));
-                const float Li = expf(-dl * dl / (2.0f * sigmaL * sigmaL));
-                Total = Total + Ci * Fi * Li;
+                const float4 tap = sDif[ly + i][lx + j];
+                const c3 Ci = mk(tap.x, tap.y, tap.z);
+                const float dl = (clum - tap.w) * (clum - tap.w);
+                const float Fi = sFi[((i + 5) / 2) * 6 + (j + 5) / 2];
+                const float Li = expf(-dl * dl * invL);
+                Total = Total + Ci * Fi * Li; // the reference's grouping: results of near-cancelled sums depend on it
                 Weight += Fi * Li;
             }
         Total = Total / Weight;
