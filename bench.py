@@ -173,10 +173,16 @@ def main():
         st = r.stats()
         rays, launches = st.primaryRays + st.extensionRays + st.shadowRays, st.launches
         if exchange:
+            xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            xa.record(stream)
             comp.composite_frame(r, rank, world, TILE_ROWS)
+            xb.record(stream)
+            xchg_events.append((xa, xb))
         r.filter_frame()
         eng.advance_frame()
         return rays, launches + 2, st
+
+    xchg_events = []
 
     def barrier():
         if world > 1:
@@ -194,6 +200,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = dict(rays=0, launches=0, ext=0.0, shd=0.0, shade=0.0, gen=0.0, acc=0.0, rep=0.0, jbf=0.0, bvh=0.0, eray=0, sray=0, pray=0, waves=0, tail=0.0, tail_eray=0, tail_paths=0, ext_launches=0)
+    xchg_events.clear()
     e0.record(stream)
     t_wall = time.perf_counter()
     for i in range(args.steps):
@@ -207,6 +214,8 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
     dev_ms = e0.elapsed_time(e1)
+    agg["xchg"] = sum(a.elapsed_time(b) for a, b in xchg_events)  # pack + all-gather (incl. waiting for the slowest rank) + unpack
+    xchg_events.clear()
     clocks = sampler.stop() if sampler else None
 
     # ---- timed: end to end through the renderer interface, host UBO in, final image out
@@ -297,7 +306,7 @@ def main():
         "rays_per_step": round(total_rays / args.steps, 0), "gpu_launches": total_launches,
         "e2e": {"value": round(total_rays_e2e / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "api": "CudaPathTracingRenderer::BeforeNextFrame + Render (host mirror of LogicRendererBase) + gk_readback(rtDenoised) to pinned memory"},
-        "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "shade", "tail", "acc", "rep", "jbf", "bvh")},
+        "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "shade", "tail", "acc", "xchg", "rep", "jbf", "bvh")},
         "tail_paths_per_step": round(agg["tail_paths"] / args.steps, 0),
         "host_gap_ms_per_step": round((wall_ms - dev_ms) / args.steps, 4),
         "bvh": {"blas_build_ms": round(info.msBlasBuild, 3), "tlas_build_ms": round(info.msTlasBuild, 3), "tlas_refit_ms": round(info.msRefit, 3), "refits_rejected": int(r.bvh_info().refitsRejected),

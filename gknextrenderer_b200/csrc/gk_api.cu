@@ -122,10 +122,11 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     c.tileRows = cfg->tileRows ? cfg->tileRows : 16;
     c.flags = cfg->flags;
     // measured on the 1080p room (sweep 16 K .. 4 M paths): the one-launch tail wins below ~2.5-3.5 K paths per SM (1 and 2 GPUs)
-    c.tailThreshold = 2560u * (uint32_t)prop.multiProcessorCount;
+    c.tailThreshold = 3584u * (uint32_t)prop.multiProcessorCount;
     if (const char* e = getenv("GK_BLAS_LEAF")) c.blasLeafMax = (uint32_t)std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("GK_SHADE_BLOCKS")) c.shadeMinBlocks = atoi(e);
     if (const char* e = getenv("GK_SAH_COLLAPSE")) c.sahCollapse = atoi(e) != 0;
+    if (const char* e = getenv("GK_TAIL_FRACTION")) c.tailFraction = (float)atof(e);
     if (const char* e = getenv("GK_TAIL_THRESHOLD")) c.tailThreshold = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("GK_COOP_THRESHOLD")) c.coopThreshold = (uint32_t)strtoul(e, nullptr, 10); // tuning / test hook
     if (c.tileIndex >= c.tileCount) {

@@ -150,6 +150,7 @@ struct Context {
     uint32_t* hCounts = nullptr; // pinned
     TraversalStats* dTravStats = nullptr;
     unsigned long long* dTailCounters = nullptr;
+    float tailFraction = 0.25f;     // ... and this fraction of the frame's paths
     uint32_t tailThreshold = 0;     // finish the frame in one launch once this few paths are alive (0: never)
     bool travStats = false;
     uint32_t blasLeafMax = 4;       // triangles per BLAS leaf (<= kBlasLeafMax)

@@ -871,13 +871,15 @@ GkStatus traceFrame(Context& c)
     spans.push_back({evStart, evGen, 0});
     uint32_t countE = n, countS = 0;
     bool tailRan = false;
+    // the tail launch pays off once the waves are short: a quarter of the paths (swept on 1, 2 and 4 GPUs), capped per SM
+    const uint32_t tailLimit = std::min(c.tailThreshold, (uint32_t)(c.tailFraction * (float)n));
     fs.tailPaths = 0;
     fs.tailExtensionRays = fs.tailShadowRays = 0;
     fs.primaryRays = (uint64_t)c.ownedRows * c.width;
     c.capturedCount = 0;
     for (uint32_t wave = 0; wave < 4096; ++wave) {
         if (countE == 0 && countS == 0) break;
-        if (wave > 0 && countE + countS <= c.tailThreshold && !c.travStats && c.captureWave < 0) {
+        if (wave > 0 && countE + countS <= tailLimit && !c.travStats && c.captureWave < 0) {
             // few paths left: finish them in one launch
             const size_t a = mark();
             GK_CUDA(cudaMemsetAsync(c.dTailCounters, 0, 2 * sizeof(unsigned long long), st));
