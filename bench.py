@@ -159,6 +159,12 @@ def main():
     stream = torch.cuda.ExternalStream(r.stream(), device=torch.device(f"cuda:{local_rank}"))
     dynamic = scene_name == "bricks"
 
+    exchange_mode = "none"
+    if world > 1:
+        exchange_mode = "nccl all-gather"
+        if os.environ.get("GK_EXCHANGE", "p2p") == "p2p" and comp.enable_peer_exchange(r, rank, world):
+            exchange_mode = "peer-to-peer push over NVLink (CUDA IPC) between two 4-byte all-reduce barriers"
+
     def frame(step_index, exchange=True):
         if dynamic:
             eng.step_scene(step_index)
@@ -301,7 +307,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[args.workload], "width": W, "height": H, "spp": settings["NumberOfSamples"], "bounces": settings["NumberOfBounces"],
                    "triangles_instanced": int(info.instancedTriangles), "triangles_unique": int(info.triangleCount), "instances": int(info.instanceCount),
-                   "partition": f"{TILE_ROWS}-row tiles interleaved over {world} rank(s), scene+BVH replicated",
+                   "partition": f"{TILE_ROWS}-row tiles interleaved over {world} rank(s), scene+BVH replicated", "exchange": exchange_mode,
                    "l2_policy": "per-frame working set (path state + queues + planes, >500 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
         "rays_per_step": round(total_rays / args.steps, 0), "gpu_launches": total_launches,
         "e2e": {"value": round(total_rays_e2e / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": int(h2d),

@@ -227,6 +227,17 @@ class Renderer:
     def exchange_unpack(self, d_all: int):
         self._check(self.lib.gk_exchange_unpack(self.h, C.c_void_p(d_all)))
 
+    def exchange_ipc_handles(self) -> bytes:
+        buf = C.create_string_buffer(N.GK_EXCHANGE_IPC_BYTES)
+        self._check(self.lib.gk_exchange_ipc_handles(self.h, buf, N.GK_EXCHANGE_IPC_BYTES))
+        return buf.raw
+
+    def exchange_open_peers(self, handles_all: bytes, world: int):
+        self._check(self.lib.gk_exchange_open_peers(self.h, handles_all, world))
+
+    def exchange_push(self):
+        self._check(self.lib.gk_exchange_push(self.h))
+
     def stream(self) -> int:
         return int(self.lib.gk_stream(self.h) or 0)
 

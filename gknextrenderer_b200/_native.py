@@ -17,6 +17,7 @@ LIB_DIR = os.path.join(_HERE, "lib")
 CUDA_LIB_PATH = os.path.join(LIB_DIR, "libgknext_cuda.so")
 HOST_LIB_PATH = os.path.join(LIB_DIR, "libgknext_host.so")
 
+GK_EXCHANGE_IPC_BYTES = 7 * 64
 GK_OK = 0
 GK_ERR_INVALID_ARGUMENT = -1
 GK_ERR_CUDA = -2
@@ -151,6 +152,9 @@ CUDA_API = {
     "gk_exchange_bytes": (C.c_size_t, [_P]),
     "gk_exchange_pack": (C.c_int, [_P, _P]),
     "gk_exchange_unpack": (C.c_int, [_P, _P]),
+    "gk_exchange_ipc_handles": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
+    "gk_exchange_open_peers": (C.c_int, [_P, C.c_void_p, C.c_uint32]),
+    "gk_exchange_push": (C.c_int, [_P]),
     "gk_host_alloc": (C.c_void_p, [C.c_size_t]),
     "gk_host_free": (None, [C.c_void_p]),
     "gk_synchronize": (C.c_int, [_P]),

@@ -92,6 +92,38 @@ def device_plane_tensor(renderer, name: str, bytes_per_pixel: int):
 
 
 _staging = {}
+_p2p = {}
+
+
+def enable_peer_exchange(renderer, rank: int, world: int, group=None) -> bool:
+    """Map the exchange planes of all ranks into this process (CUDA IPC) so that composite_frame can
+    push rows straight into the peers.  Returns False (and keeps the NCCL all-gather path) when the
+    handles cannot be opened, e.g. no peer access between the devices."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return False
+    from . import _native as N
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    mine = torch.frombuffer(bytearray(renderer.exchange_ipc_handles()), dtype=torch.uint8).to(dev)
+    every = torch.empty(world * N.GK_EXCHANGE_IPC_BYTES, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    ok = True
+    try:
+        renderer.exchange_open_peers(bytes(every.cpu().numpy().tobytes()), world)
+    except Exception as e:  # noqa: BLE001
+        print(f"[compositor] rank {rank}: peer mapping unavailable ({e}); using the NCCL all-gather exchange", flush=True)
+        ok = False
+    # all ranks must take the same path
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    ok = bool(int(flag.item()))
+    key = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if ok:
+        _p2p[key] = (torch.zeros(1, dtype=torch.int32, device=dev), torch.cuda.ExternalStream(renderer.stream(), device=dev))
+    else:
+        _p2p.pop(key, None)
+    return ok
 
 
 def composite_frame(renderer, rank: int, world: int, tile_rows: int, planes=None, group=None):
@@ -103,6 +135,18 @@ def composite_frame(renderer, rank: int, world: int, tile_rows: int, planes=None
     import torch.distributed as dist
     if world == 1:
         return 0
+    hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if hkey in _p2p:
+        # peer-to-peer: barrier (every rank is done reading last frame's planes) -> one kernel stores the
+        # owned rows into all peers over NVLink -> barrier (all rows have landed).  The barriers are
+        # 4-byte all-reduces ordered on the library's stream.
+        token, stream = _p2p[hkey]
+        with torch.cuda.stream(stream):
+            dist.all_reduce(token, group=group)
+        renderer.exchange_push()
+        with torch.cuda.stream(stream):
+            dist.all_reduce(token, group=group)
+        return renderer.exchange_bytes()
     nbytes = renderer.exchange_bytes()
     key = (renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h), nbytes, world)
     if key not in _staging:

@@ -384,6 +384,24 @@ GkStatus gk_exchange_unpack(GkContext* ctx, const void* d_all)
     return exchangeUnpack(c, d_all);
 }
 
+GkStatus gk_exchange_ipc_handles(GkContext* ctx, void* out, size_t bytes)
+{
+    GK_CHECK_CTX(ctx);
+    return exchangeIpcHandles(c, out, bytes);
+}
+
+GkStatus gk_exchange_open_peers(GkContext* ctx, const void* handles_all, uint32_t world)
+{
+    GK_CHECK_CTX(ctx);
+    return exchangeOpenPeers(c, handles_all, world);
+}
+
+GkStatus gk_exchange_push(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    return exchangePush(c);
+}
+
 void* gk_host_alloc(size_t bytes)
 {
     void* p = nullptr;

@@ -69,6 +69,18 @@ struct ModelInfo { // per Assets::Model
     float bmin[4], bmax[4];           // BLAS root box (BVH::aabbMin/aabbMax)
 };
 
+// Peer-to-peer frame exchange (multi-GPU, one process per GPU): the exchange planes of the other ranks,
+// opened through CUDA IPC, so that one kernel can store this rank's rows straight into every peer.
+constexpr int kMaxPeers = 16;
+constexpr int kPeerBuffers = 7; // the six exchange planes + the second object-id buffer (the two swap every frame)
+struct PeerExchange {
+    bool open = false;
+    uint32_t world = 0;
+    void* base[kMaxPeers][kPeerBuffers] = {};
+    void* myId0 = nullptr; // this rank's object-id buffers as they were exported
+    void* myId1 = nullptr;
+};
+
 struct Planes {
     void* p[GK_PLANE_COUNT] = {};
     size_t bytes[GK_PLANE_COUNT] = {};
@@ -159,6 +171,7 @@ struct Context {
     cudaEvent_t evA = nullptr, evB = nullptr;
     std::vector<cudaEvent_t> evPool;
     int captureWave = -1;
+    PeerExchange peers;
     float tlasAreaAtBuild = 0.f;    // summed internal-node area of the TLAS when it was last built
     uint32_t refitRejected = 0;     // refits that degraded the tree too much and became rebuilds
     DevBuf<uint32_t> dRootRef;
@@ -196,6 +209,10 @@ void applyPendingHistorySwap(Context& c);
 size_t exchangeBytesPerRank(const Context& c);
 GkStatus exchangePack(Context& c, void* dStaging);
 GkStatus exchangeUnpack(Context& c, const void* dAll);
+GkStatus exchangeIpcHandles(Context& c, void* out, size_t bytes);
+GkStatus exchangeOpenPeers(Context& c, const void* handlesAll, uint32_t world);
+GkStatus exchangePush(Context& c);
+void exchangeClosePeers(Context& c);
 
 } // namespace gk
 

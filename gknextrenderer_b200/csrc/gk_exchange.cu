@@ -67,7 +67,117 @@ ExchangeArgs makeArgs(const Context& c)
     return A;
 }
 
+// Peer-to-peer variant: one launch stores the rows this rank owns straight into the planes of every
+// other rank over NVLink (no staging buffer, no unpack).  grid = (chunks of a row, owned rows, planes).
+struct PushArgs {
+    const uint32_t* src[kExchangePlanes];
+    uint32_t* dst[kMaxPeers][kExchangePlanes];
+    uint32_t words[kExchangePlanes];
+    uint32_t width, height, tileRows, tileCount, tileIndex, peers;
+};
+
+__global__ void __launch_bounds__(256) k_exchange_push(PushArgs A)
+{
+    const uint32_t p = blockIdx.z, lrow = blockIdx.y;
+    const uint32_t row = ((lrow / A.tileRows) * A.tileCount + A.tileIndex) * A.tileRows + lrow % A.tileRows;
+    if (row >= A.height) return;
+    const uint32_t rowWords = A.width * A.words[p];
+    const uint64_t base = (uint64_t)row * rowWords;
+    if ((rowWords & 3u) == 0) { // 128-bit path (every plane base is 256-byte aligned)
+        const uint4* s = reinterpret_cast<const uint4*>(A.src[p] + base);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rowWords / 4; i += gridDim.x * blockDim.x) {
+            const uint4 v = s[i];
+            for (uint32_t r = 0; r < A.peers; ++r)
+                if (r != A.tileIndex) reinterpret_cast<uint4*>(A.dst[r][p] + base)[i] = v;
+        }
+    } else {
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rowWords; i += gridDim.x * blockDim.x) {
+            const uint32_t v = A.src[p][base + i];
+            for (uint32_t r = 0; r < A.peers; ++r)
+                if (r != A.tileIndex) A.dst[r][p][base + i] = v;
+        }
+    }
+}
+
 } // namespace
+
+GkStatus exchangeIpcHandles(Context& c, void* out, size_t bytes)
+{
+    if (!out || bytes < kPeerBuffers * sizeof(cudaIpcMemHandle_t)) {
+        setLastError("gk_exchange_ipc_handles: buffer too small");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    applyPendingHistorySwap(c);
+    cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(out);
+    for (int p = 0; p < kExchangePlanes; ++p) GK_CUDA(cudaIpcGetMemHandle(&h[p], c.planes.p[kPlaneIds[p]]));
+    GK_CUDA(cudaIpcGetMemHandle(&h[kExchangePlanes], c.planes.p[GK_PLANE_OBJECT_ID1]));
+    c.peers.myId0 = c.planes.p[GK_PLANE_OBJECT_ID0], c.peers.myId1 = c.planes.p[GK_PLANE_OBJECT_ID1];
+    return GK_OK;
+}
+
+void exchangeClosePeers(Context& c)
+{
+    if (!c.peers.open) return;
+    for (uint32_t r = 0; r < c.peers.world; ++r)
+        for (int b = 0; b < kPeerBuffers; ++b)
+            if (c.peers.base[r][b]) cudaIpcCloseMemHandle(c.peers.base[r][b]), c.peers.base[r][b] = nullptr;
+    c.peers.open = false;
+}
+
+GkStatus exchangeOpenPeers(Context& c, const void* handlesAll, uint32_t world)
+{
+    if (!handlesAll || world != c.tileCount || world > (uint32_t)kMaxPeers) {
+        setLastError("gk_exchange_open_peers: world must equal GkConfig.tileCount (<= 16)");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    if (!c.peers.myId0) {
+        setLastError("gk_exchange_open_peers: call gk_exchange_ipc_handles first");
+        return GK_ERR_NOT_READY;
+    }
+    exchangeClosePeers(c);
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handlesAll);
+    c.peers.world = world;
+    for (uint32_t r = 0; r < world; ++r) {
+        if (r == c.tileIndex) continue;
+        for (int b = 0; b < kPeerBuffers; ++b) {
+            const cudaError_t e = cudaIpcOpenMemHandle(&c.peers.base[r][b], h[r * kPeerBuffers + b], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                c.peers.open = true; // so that the handles opened so far are closed
+                exchangeClosePeers(c);
+                setLastError(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+                return GK_ERR_CUDA;
+            }
+        }
+    }
+    c.peers.open = true;
+    return GK_OK;
+}
+
+GkStatus exchangePush(Context& c)
+{
+    if (!c.peers.open) {
+        setLastError("gk_exchange_push: peers not opened");
+        return GK_ERR_NOT_READY;
+    }
+    PushArgs A;
+    A.width = c.width, A.height = c.height, A.tileRows = c.tileRows, A.tileCount = c.tileCount, A.tileIndex = c.tileIndex, A.peers = c.peers.world;
+    // The two object-id buffers trade places every frame on every rank alike: address the peer's
+    // buffer that plays the role of ObjectId0 this frame.
+    const bool idSwapped = c.planes.p[GK_PLANE_OBJECT_ID0] != c.peers.myId0;
+    for (int p = 0; p < kExchangePlanes; ++p) {
+        A.src[p] = (const uint32_t*)c.planes.p[kPlaneIds[p]];
+        A.words[p] = kPlaneWords[p];
+        const int slot = (kPlaneIds[p] == GK_PLANE_OBJECT_ID0 && idSwapped) ? kExchangePlanes : p;
+        for (uint32_t r = 0; r < c.peers.world; ++r) A.dst[r][p] = (uint32_t*)c.peers.base[r][slot];
+    }
+    const uint32_t blocksPerRank = (c.height + c.tileRows * c.tileCount - 1) / (c.tileRows * c.tileCount);
+    const dim3 grid((c.width * 2 / 4 + 255) / 256, blocksPerRank * c.tileRows, kExchangePlanes);
+    k_exchange_push<<<grid, 256, 0, c.stream>>>(A);
+    GK_CUDA(cudaGetLastError());
+    c.stats.launches += 1;
+    return GK_OK;
+}
 
 size_t exchangeBytesPerRank(const Context& c) { return (size_t)makeArgs(c).rankWords * 4; }
 

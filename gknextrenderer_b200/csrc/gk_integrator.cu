@@ -725,6 +725,8 @@ template <class T> static cudaError_t allocInto(std::vector<void*>& pool, T*& p,
 
 void freeFrameResources(Context& c)
 {
+    exchangeClosePeers(c); // the mapped peer planes belong to the extent being torn down
+    c.peers.myId0 = c.peers.myId1 = nullptr;
     for (void* p : c.pathAllocs) cudaFree(p);
     for (void* p : c.queueAllocs) cudaFree(p);
     c.pathAllocs.clear(), c.queueAllocs.clear();

@@ -176,6 +176,17 @@ size_t gk_exchange_bytes(const GkContext* ctx);
 GkStatus gk_exchange_pack(GkContext* ctx, void* d_staging);
 GkStatus gk_exchange_unpack(GkContext* ctx, const void* d_all);
 
+/* Peer-to-peer form of the same exchange (one process per GPU on one NVLink/NVSwitch node):
+ *   gk_exchange_ipc_handles  writes GK_EXCHANGE_IPC_BYTES bytes of CUDA IPC handles of this context's exchange planes;
+ *   gk_exchange_open_peers   takes the handles of all `world` ranks (rank-major, world == GkConfig.tileCount) and maps them;
+ *   gk_exchange_push         one kernel stores the rows this rank owns into the planes of every peer.
+ * The caller orders it between two cross-rank barriers on gk_stream(): peers must have finished
+ * filtering the previous frame before the push, and all pushes must have landed before gk_filter_frame. */
+#define GK_EXCHANGE_IPC_BYTES (7 * 64)
+GkStatus gk_exchange_ipc_handles(GkContext* ctx, void* out, size_t bytes);
+GkStatus gk_exchange_open_peers(GkContext* ctx, const void* handles_all, uint32_t world);
+GkStatus gk_exchange_push(GkContext* ctx);
+
 /* Page-locked host memory for arrays that are uploaded every frame (the node proxies: the reference
  * writes them straight into a mapped device buffer, src/Assets/Scene.cpp:464-511).  Returns NULL when
  * no CUDA device is usable; the caller then keeps using ordinary memory. */

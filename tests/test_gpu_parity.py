@@ -434,3 +434,22 @@ def test_both_ray_to_lane_mappings_give_identical_hits(built, threshold, monkeyp
     o = orc.render(ubo, 160, 90, threads=os.cpu_count() or 1)
     assert _gbuffer_check(r, o, f"cornell threshold={threshold}").all()
     _radiance_check(r, o, f"cornell threshold={threshold}", 160, 90)
+
+
+# ---------------------------------------------------------------- multi-GPU (needs >= 2 devices on the box)
+@pytest.mark.gpu
+def test_two_gpu_tile_frame_equals_single_gpu_frame(built):
+    """tools/multi_gpu_check.py under torchrun: tile-partitioned trace + frame-end exchange (peer-to-peer
+    push, then the NCCL all-gather form) must reproduce the single-GPU image bit for bit."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for mode, port in (("p2p", 29531), ("nccl", 29532)):
+        env = dict(os.environ, GK_EXCHANGE=mode)
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+                              os.path.join(root, "tools", "multi_gpu_check.py")], env=env, capture_output=True, text=True, timeout=300)
+        print(out.stdout[-2000:])
+        assert out.returncode == 0 and "MULTI_GPU_CHECK PASS" in out.stdout, out.stderr[-2000:]
