@@ -37,13 +37,14 @@ WORKLOADS = {
     "room": ("room", (1000000, 1234), 1920, 1080, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
     "cornell": ("cornell", (), 640, 360, dict(NumberOfSamples=8, NumberOfBounces=4, TemporalFrames=16, Denoiser=0, TAA=0, ProgressiveRender=1)),
     "bricks": ("bricks", (200000, 42), 1920, 1080, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
-    "city": ("city", (40, 100, 7, 46), 3840, 2160, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
+    # progressive accumulation, denoiser off: the state gkNextBenchmark runs in (gkNextBenchmark.cpp:16-31); one step = 1 of the 64 spp
+    "city": ("city", (40, 100, 7, 46), 3840, 2160, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=0, TAA=0, ProgressiveRender=1)),
 }
 WORKLOAD_NAMES = {
     "room": "C2: procedural 1M-triangle room (1280 instances of 6 meshes), 1920x1080, 1 spp, 4 bounces, sun+sky, reproject + JBF",
     "cornell": "C1: built-in Cornell box, 640x360, 8 spp, 4 bounces",
     "bricks": "C3: 200k instanced bricks, per-frame TLAS refit, 1920x1080, 1 spp, 4 bounces",
-    "city": "C4: 10M-triangle instanced city, 3840x2160, 1 spp per step, 4 bounces",
+    "city": "C4: 10M-triangle instanced city, 3840x2160, progressive (1 of 64 spp per step), 4 bounces, denoiser off",
 }
 TILE_ROWS = 16
 
@@ -165,6 +166,10 @@ def main():
         if os.environ.get("GK_EXCHANGE", "p2p") == "p2p" and comp.enable_peer_exchange(r, rank, world):
             exchange_mode = "peer-to-peer push over NVLink (CUDA IPC) between two 4-byte all-reduce barriers"
 
+    local_filters = world > 1 and exchange_mode.startswith("peer") and settings.get("ProgressiveRender", 0) == 1 and settings.get("Denoiser", 1) == 0
+    if local_filters:
+        exchange_mode = "filters on owned rows; final image rows pushed peer-to-peer over NVLink to every rank between two 4-byte all-reduce barriers"
+
     def frame(step_index, exchange=True):
         if dynamic:
             eng.step_scene(step_index)
@@ -178,6 +183,17 @@ def main():
         r.trace_frame()
         st = r.stats()
         rays, launches = st.primaryRays + st.extensionRays + st.shadowRays, st.launches
+        if local_filters:
+            # progressive, no denoiser: per-pixel filters on the owned rows, then only the final image travels
+            r.filter_frame_owned()
+            if exchange:
+                xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                xa.record(stream)
+                comp.composite_final(r, rank, world, -1)
+                xb.record(stream)
+                xchg_events.append((xa, xb))
+            eng.advance_frame()
+            return rays, launches + 1, st
         if exchange:
             xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             xa.record(stream)

@@ -235,6 +235,12 @@ class Renderer:
     def exchange_open_peers(self, handles_all: bytes, world: int):
         self._check(self.lib.gk_exchange_open_peers(self.h, handles_all, world))
 
+    def filter_frame_owned(self):
+        self._check(self.lib.gk_filter_frame_owned(self.h))
+
+    def exchange_push_final(self, dst_rank: int = -1):
+        self._check(self.lib.gk_exchange_push_final(self.h, dst_rank))
+
     def exchange_push(self):
         self._check(self.lib.gk_exchange_push(self.h))
 

@@ -17,7 +17,7 @@ LIB_DIR = os.path.join(_HERE, "lib")
 CUDA_LIB_PATH = os.path.join(LIB_DIR, "libgknext_cuda.so")
 HOST_LIB_PATH = os.path.join(LIB_DIR, "libgknext_host.so")
 
-GK_EXCHANGE_IPC_BYTES = 7 * 64
+GK_EXCHANGE_IPC_BYTES = 8 * 64
 GK_OK = 0
 GK_ERR_INVALID_ARGUMENT = -1
 GK_ERR_CUDA = -2
@@ -155,6 +155,8 @@ CUDA_API = {
     "gk_exchange_ipc_handles": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "gk_exchange_open_peers": (C.c_int, [_P, C.c_void_p, C.c_uint32]),
     "gk_exchange_push": (C.c_int, [_P]),
+    "gk_filter_frame_owned": (C.c_int, [_P]),
+    "gk_exchange_push_final": (C.c_int, [_P, C.c_int]),
     "gk_host_alloc": (C.c_void_p, [C.c_size_t]),
     "gk_host_free": (None, [C.c_void_p]),
     "gk_synchronize": (C.c_int, [_P]),

@@ -160,3 +160,24 @@ def composite_frame(renderer, rank: int, world: int, tile_rows: int, planes=None
         dist.all_gather_into_tensor(recv, send, group=group)
     renderer.exchange_unpack(recv.data_ptr())
     return nbytes
+
+
+def composite_final(renderer, rank: int, world: int, dst_rank: int = -1, group=None):
+    """Progressive frames without the denoiser are filtered per pixel on the rank that traced them
+    (Renderer.filter_frame_owned), so only the finished image travels: the owned rows of rtDenoised
+    (8 B/pixel instead of 44) are stored into rank `dst_rank` (-1: all ranks) between two stream barriers.
+    Needs enable_peer_exchange()."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return 0
+    hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if hkey not in _p2p:
+        raise RuntimeError("composite_final needs enable_peer_exchange() to have succeeded")
+    token, stream = _p2p[hkey]
+    with torch.cuda.stream(stream):
+        dist.all_reduce(token, group=group)
+    renderer.exchange_push_final(dst_rank)
+    with torch.cuda.stream(stream):
+        dist.all_reduce(token, group=group)
+    return renderer.plane_bytes("DENOISED") // world

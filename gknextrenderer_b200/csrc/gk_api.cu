@@ -396,6 +396,18 @@ GkStatus gk_exchange_open_peers(GkContext* ctx, const void* handles_all, uint32_
     return exchangeOpenPeers(c, handles_all, world);
 }
 
+GkStatus gk_filter_frame_owned(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    return filterFrameOwnedRows(c);
+}
+
+GkStatus gk_exchange_push_final(GkContext* ctx, int dst_rank)
+{
+    GK_CHECK_CTX(ctx);
+    return exchangePushFinal(c, dst_rank);
+}
+
 GkStatus gk_exchange_push(GkContext* ctx)
 {
     GK_CHECK_CTX(ctx);

@@ -72,7 +72,7 @@ struct ModelInfo { // per Assets::Model
 // Peer-to-peer frame exchange (multi-GPU, one process per GPU): the exchange planes of the other ranks,
 // opened through CUDA IPC, so that one kernel can store this rank's rows straight into every peer.
 constexpr int kMaxPeers = 16;
-constexpr int kPeerBuffers = 7; // the six exchange planes + the second object-id buffer (the two swap every frame)
+constexpr int kPeerBuffers = 8; // the six exchange planes, the second object-id buffer (the two swap every frame), rtDenoised
 struct PeerExchange {
     bool open = false;
     uint32_t world = 0;
@@ -212,6 +212,8 @@ GkStatus exchangeUnpack(Context& c, const void* dAll);
 GkStatus exchangeIpcHandles(Context& c, void* out, size_t bytes);
 GkStatus exchangeOpenPeers(Context& c, const void* handlesAll, uint32_t world);
 GkStatus exchangePush(Context& c);
+GkStatus exchangePushFinal(Context& c, int dstRank);
+GkStatus filterFrameOwnedRows(Context& c);
 void exchangeClosePeers(Context& c);
 
 } // namespace gk

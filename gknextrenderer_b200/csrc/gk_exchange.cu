@@ -74,6 +74,7 @@ struct PushArgs {
     uint32_t* dst[kMaxPeers][kExchangePlanes];
     uint32_t words[kExchangePlanes];
     uint32_t width, height, tileRows, tileCount, tileIndex, peers;
+    uint32_t peerMask; // destination ranks
 };
 
 __global__ void __launch_bounds__(256) k_exchange_push(PushArgs A)
@@ -88,13 +89,13 @@ __global__ void __launch_bounds__(256) k_exchange_push(PushArgs A)
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rowWords / 4; i += gridDim.x * blockDim.x) {
             const uint4 v = s[i];
             for (uint32_t r = 0; r < A.peers; ++r)
-                if (r != A.tileIndex) reinterpret_cast<uint4*>(A.dst[r][p] + base)[i] = v;
+                if ((A.peerMask >> r) & 1u) reinterpret_cast<uint4*>(A.dst[r][p] + base)[i] = v;
         }
     } else {
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rowWords; i += gridDim.x * blockDim.x) {
             const uint32_t v = A.src[p][base + i];
             for (uint32_t r = 0; r < A.peers; ++r)
-                if (r != A.tileIndex) A.dst[r][p][base + i] = v;
+                if ((A.peerMask >> r) & 1u) A.dst[r][p][base + i] = v;
         }
     }
 }
@@ -111,6 +112,7 @@ GkStatus exchangeIpcHandles(Context& c, void* out, size_t bytes)
     cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(out);
     for (int p = 0; p < kExchangePlanes; ++p) GK_CUDA(cudaIpcGetMemHandle(&h[p], c.planes.p[kPlaneIds[p]]));
     GK_CUDA(cudaIpcGetMemHandle(&h[kExchangePlanes], c.planes.p[GK_PLANE_OBJECT_ID1]));
+    GK_CUDA(cudaIpcGetMemHandle(&h[kExchangePlanes + 1], c.planes.p[GK_PLANE_DENOISED]));
     c.peers.myId0 = c.planes.p[GK_PLANE_OBJECT_ID0], c.peers.myId1 = c.planes.p[GK_PLANE_OBJECT_ID1];
     return GK_OK;
 }
@@ -162,6 +164,7 @@ GkStatus exchangePush(Context& c)
     }
     PushArgs A;
     A.width = c.width, A.height = c.height, A.tileRows = c.tileRows, A.tileCount = c.tileCount, A.tileIndex = c.tileIndex, A.peers = c.peers.world;
+    A.peerMask = ((1u << c.peers.world) - 1u) & ~(1u << c.tileIndex);
     // The two object-id buffers trade places every frame on every rank alike: address the peer's
     // buffer that plays the role of ObjectId0 this frame.
     const bool idSwapped = c.planes.p[GK_PLANE_OBJECT_ID0] != c.peers.myId0;
@@ -173,6 +176,32 @@ GkStatus exchangePush(Context& c)
     }
     const uint32_t blocksPerRank = (c.height + c.tileRows * c.tileCount - 1) / (c.tileRows * c.tileCount);
     const dim3 grid((c.width * 2 / 4 + 255) / 256, blocksPerRank * c.tileRows, kExchangePlanes);
+    k_exchange_push<<<grid, 256, 0, c.stream>>>(A);
+    GK_CUDA(cudaGetLastError());
+    c.stats.launches += 1;
+    return GK_OK;
+}
+
+GkStatus exchangePushFinal(Context& c, int dstRank)
+{
+    if (!c.peers.open) {
+        setLastError("gk_exchange_push_final: peers not opened");
+        return GK_ERR_NOT_READY;
+    }
+    if (dstRank >= (int)c.peers.world) {
+        setLastError("gk_exchange_push_final: dst_rank out of range");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    PushArgs A{};
+    A.width = c.width, A.height = c.height, A.tileRows = c.tileRows, A.tileCount = c.tileCount, A.tileIndex = c.tileIndex, A.peers = c.peers.world;
+    A.peerMask = dstRank < 0 ? ((1u << c.peers.world) - 1u) : (1u << dstRank);
+    A.peerMask &= ~(1u << c.tileIndex);
+    if (A.peerMask == 0) return GK_OK; // the destination is this rank: its rows are already in place
+    A.src[0] = (const uint32_t*)c.planes.p[GK_PLANE_DENOISED];
+    A.words[0] = 2;
+    for (uint32_t r = 0; r < c.peers.world; ++r) A.dst[r][0] = (uint32_t*)c.peers.base[r][kExchangePlanes + 1];
+    const uint32_t blocksPerRank = (c.height + c.tileRows * c.tileCount - 1) / (c.tileRows * c.tileCount);
+    const dim3 grid((c.width * 2 / 4 + 255) / 256, blocksPerRank * c.tileRows, 1);
     k_exchange_push<<<grid, 256, 0, c.stream>>>(A);
     GK_CUDA(cudaGetLastError());
     c.stats.launches += 1;

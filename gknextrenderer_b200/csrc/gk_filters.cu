@@ -26,6 +26,19 @@ namespace {
 
 constexpr int TX = 32, TY = 8;
 
+// Row ownership of a tile-partitioned frame (GkConfig): count == 1 means "every row".
+struct RowTiles {
+    uint32_t index, count, rows;
+    __device__ __forceinline__ bool owns(int y) const { return count <= 1u || ((uint32_t)y / rows) % count == index; }
+    __device__ __forceinline__ bool ownsAny(int y0, int n) const
+    {
+        if (count <= 1u) return true;
+        for (int i = 0; i < n; ++i)
+            if (owns(y0 + i)) return true;
+        return false;
+    }
+};
+
 struct c3 {
     float x, y, z;
 };
@@ -86,6 +99,7 @@ struct ReprojectArgs {
     const uint32_t* id1;
     const uint2* normal;
     int W, H;
+    RowTiles tiles; // rows to produce (the whole frame unless gk_filter_frame_owned)
 };
 
 constexpr int RH = 2; // halo of the 5x5 windows
@@ -101,6 +115,7 @@ __global__ void __launch_bounds__(TX* TY) k_reproject(const GkUniformBufferObjec
     const int W = A.W, H = A.H;
     const int vx = (int)U.ViewportRect[0], vy = (int)U.ViewportRect[1];
     const int bx = blockIdx.x * TX + vx, by = blockIdx.y * TY + vy;
+    if (!A.tiles.ownsAny(by, TY)) return;
     const bool progressive = U.ProgressiveRender != 0;
     if (!progressive) {
         for (int i = threadIdx.y * TX + threadIdx.x; i < RW * RHT; i += TX * TY) {
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(TX* TY) k_reproject(const GkUniformBufferObjec
         __syncthreads();
     }
     const int x = bx + threadIdx.x, y = by + threadIdx.y;
-    if (x >= W || y >= H) return;
+    if (x >= W || y >= H || !A.tiles.owns(y)) return;
     const size_t pi = (size_t)y * W + x;
     if (progressive) { // ReProject:76-82
         const float t = clampx(1.0f / float(U.TemporalFrames), 0.0f, 1.0f);
@@ -261,6 +276,7 @@ struct DenoiseArgs {
     const uint32_t* id1;
     uint2* out; // rtDenoised
     int W, H;
+    RowTiles tiles;
 };
 
 constexpr int DH = 5;
@@ -274,6 +290,7 @@ __global__ void __launch_bounds__(TX* TY) k_denoise_jbf(const GkUniformBufferObj
     const int W = A.W, H = A.H;
     const int vx = (int)U.ViewportRect[0], vy = (int)U.ViewportRect[1];
     const int bx = blockIdx.x * TX + vx, by = blockIdx.y * TY + vy;
+    if (!A.tiles.ownsAny(by, TY)) return;
     const bool filter = U.BFSize > 0;
     if (filter) {
         const int t = threadIdx.y * TX + threadIdx.x;
@@ -290,7 +307,7 @@ __global__ void __launch_bounds__(TX* TY) k_denoise_jbf(const GkUniformBufferObj
         __syncthreads();
     }
     const int x = bx + threadIdx.x, y = by + threadIdx.y;
-    if (x >= W || y >= H) return;
+    if (x >= W || y >= H || !A.tiles.owns(y)) return;
     const size_t pi = (size_t)y * W + x;
     const c3 bias = mk(0.001f, 0.001f, 0.001f);
     c3 Total = mk(0, 0, 0);
@@ -339,7 +356,22 @@ __global__ void __launch_bounds__(TX* TY) k_denoise_jbf(const GkUniformBufferObj
 
 } // namespace
 
-GkStatus filterFrame(Context& c)
+static GkStatus runFilters(Context& c, bool ownedRowsOnly);
+
+GkStatus filterFrame(Context& c) { return runFilters(c, false); }
+
+// Tile-partitioned progressive frames: every pass is per pixel (ReProject:76-82, DenoiseJBF with BFSize == 0),
+// so each rank accumulates and composes only the rows it traced; history stays on the rank that owns the row.
+GkStatus filterFrameOwnedRows(Context& c)
+{
+    if (c.haveUbo && c.tileCount > 1 && !(c.ubo.ProgressiveRender != 0 && c.ubo.BFSize == 0)) {
+        setLastError("gk_filter_frame_owned: needs ProgressiveRender != 0 and BFSize == 0 (the spatial passes read rows of other ranks)");
+        return GK_ERR_UNSUPPORTED;
+    }
+    return runFilters(c, true);
+}
+
+static GkStatus runFilters(Context& c, bool ownedRowsOnly)
 {
     if (!c.haveUbo) {
         setLastError("gk_filter_frame: UBO must be set first");
@@ -359,6 +391,7 @@ GkStatus filterFrame(Context& c)
     R.motion = (const float2*)P[GK_PLANE_MOTION], R.id0 = (const uint32_t*)P[GK_PLANE_OBJECT_ID0], R.id1 = (const uint32_t*)P[GK_PLANE_OBJECT_ID1];
     R.normal = (const uint2*)P[GK_PLANE_NORMAL];
     R.W = (int)c.width, R.H = (int)c.height;
+    R.tiles = ownedRowsOnly ? RowTiles{c.tileIndex, c.tileCount, c.tileRows} : RowTiles{0, 1, 1};
     const dim3 block(TX, TY), grid((c.width + TX - 1) / TX, (c.height + TY - 1) / TY);
     cudaEventRecord(e0, st);
     k_reproject<<<grid, block, 0, st>>>(c.dUbo, R);
@@ -366,6 +399,7 @@ GkStatus filterFrame(Context& c)
     DenoiseArgs D;
     D.diffuse = R.out[0], D.spec = R.out[1], D.albedo = R.out[2], D.id0 = R.id0, D.id1 = R.id1, D.out = (uint2*)P[GK_PLANE_DENOISED];
     D.W = R.W, D.H = R.H;
+    D.tiles = R.tiles;
     k_denoise_jbf<<<grid, block, 0, st>>>(c.dUbo, D);
     cudaEventRecord(e2, st);
     GK_CUDA(cudaGetLastError());

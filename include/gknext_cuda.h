@@ -182,10 +182,17 @@ GkStatus gk_exchange_unpack(GkContext* ctx, const void* d_all);
  *   gk_exchange_push         one kernel stores the rows this rank owns into the planes of every peer.
  * The caller orders it between two cross-rank barriers on gk_stream(): peers must have finished
  * filtering the previous frame before the push, and all pushes must have landed before gk_filter_frame. */
-#define GK_EXCHANGE_IPC_BYTES (7 * 64)
+#define GK_EXCHANGE_IPC_BYTES (8 * 64)
 GkStatus gk_exchange_ipc_handles(GkContext* ctx, void* out, size_t bytes);
 GkStatus gk_exchange_open_peers(GkContext* ctx, const void* handles_all, uint32_t world);
 GkStatus gk_exchange_push(GkContext* ctx);
+/* Progressive rendering without the denoiser (the state gkNextBenchmark runs in, gkNextBenchmark.cpp:16-31)
+ * filters every pixel on its own, so a tile-partitioned frame needs no exchange before the filters:
+ *   gk_filter_frame_owned     runs the accumulate + compose passes on the rows this context owns
+ *                             (GK_ERR_UNSUPPORTED unless ProgressiveRender != 0 and BFSize == 0);
+ *   gk_exchange_push_final    stores the owned rows of rtDenoised into rank `dst_rank` (-1: every peer). */
+GkStatus gk_filter_frame_owned(GkContext* ctx);
+GkStatus gk_exchange_push_final(GkContext* ctx, int dst_rank);
 
 /* Page-locked host memory for arrays that are uploaded every frame (the node proxies: the reference
  * writes them straight into a mapped device buffer, src/Assets/Scene.cpp:464-511).  Returns NULL when
