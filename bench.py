@@ -61,12 +61,51 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs (the clocks line of
+    B200_PROFILING.md): an NVML polling thread (every 10 ms), nvidia-smi -lms as the fallback."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
+        import threading
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = threading.Event()
+        self.thread, self.p, self.f = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+            self._start_smi(gpu_index)
+
+    def _poll(self):
+        nv = self.nv
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                if get_reasons:
+                    mask = int(get_reasons(self.h))
+                    for label, a, b in names:
+                        bit = getattr(nv, a, None) or getattr(nv, b, None)
+                        if bit and (mask & int(bit)):
+                            self.reasons.add(label)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _start_smi(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
@@ -75,6 +114,12 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.sm:
+                out = {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -98,7 +143,7 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.f.name)
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
         return out
 
 
@@ -297,10 +342,20 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        pass
     px = W * H
     filt_ms = (agg["rep"] + agg["jbf"]) / args.steps
     roofline = {"kernel": "k_trace<closest hit> (extend: traversal of the 8-wide quantised two-level BVH)", "bound": "l2", "achieved": round(achieved, 1), "peak": round(l2_peak, 1), "unit": "GB/s",
-                "frac": round(achieved / l2_peak, 4) if l2_peak else None, "traffic": None,
+                "frac": round(achieved / l2_peak, 4) if l2_peak else None,
+                "traffic": traffic.get("dram_bytes_per_launch_avg") if args.workload == "room" and world == 1 else None,
+                "traffic_source": traffic.get("source") if args.workload == "room" and world == 1 else None,
+                "algorithmic_bytes_per_launch": round(bytes_per_ray * ext_rays / max(agg["ext_launches"], 1), 0),
+                "note": "achieved = L2-level algorithmic bytes (48 B ray/hit + 128 B per node visit + 48 B per triangle test, counted by an instrumented frame) / kernel time; "
+                        "traffic = DRAM bytes per launch from ncu: only the compulsory 52 B/ray reach HBM, the node/triangle bytes are served by L1/L2 (SURVEY 8d: this kernel is L2/issue bound)",
                 "model": {"bytes_per_ray": round(bytes_per_ray, 1), "node_visits_per_ray": round(nodes_per_ray, 2), "tri_tests_per_ray": round(tris_per_ray, 2),
                           "rays_per_launch_avg": round(ext_rays / max(agg["ext_launches"], 1), 0), "launches_per_step": round(agg["ext_launches"] / args.steps, 1), "ms_per_step": round(ext_ms / args.steps, 4),
                           "Grays_per_s_in_kernel": round(ext_rays / (ext_ms * 1e-3) / 1e9, 4) if ext_ms > 0 else None},
