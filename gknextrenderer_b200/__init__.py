@@ -210,6 +210,13 @@ class Renderer:
         self._check(self.lib.gk_readback(self.h, PLANES[name], out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
+    def readback_async(self, name, dst_ptr: int, nbytes: int):
+        """Queue a device->host copy of a plane behind the submitted work (dst should be pinned memory)."""
+        self._check(self.lib.gk_readback_async(self.h, PLANES[name], C.c_void_p(dst_ptr), nbytes))
+
+    def readback_wait(self):
+        self._check(self.lib.gk_readback_wait(self.h))
+
     def upload_plane(self, name, arr: np.ndarray):
         arr = np.ascontiguousarray(arr)
         assert arr.nbytes == self.plane_bytes(name), (arr.nbytes, self.plane_bytes(name))

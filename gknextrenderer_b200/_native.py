@@ -147,6 +147,8 @@ CUDA_API = {
     "gk_intersect_device": (C.c_int, [_P, _P, C.c_uint32, _P, _P, C.c_int]),
     "gk_plane_bytes": (C.c_size_t, [_P, C.c_int]),
     "gk_readback": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "gk_readback_async": (C.c_int, [_P, C.c_int, C.c_void_p, C.c_size_t]),
+    "gk_readback_wait": (C.c_int, [_P]),
     "gk_upload_plane": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "gk_plane_device": (_P, [_P, C.c_int]),
     "gk_exchange_bytes": (C.c_size_t, [_P]),

@@ -141,6 +141,7 @@ def composite_frame(renderer, rank: int, world: int, tile_rows: int, planes=None
         # owned rows into all peers over NVLink -> barrier (all rows have landed).  The barriers are
         # 4-byte all-reduces ordered on the library's stream.
         token, stream = _p2p[hkey]
+        renderer.readback_wait()  # peers are about to overwrite planes an asynchronous read-back may still be reading
         with torch.cuda.stream(stream):
             dist.all_reduce(token, group=group)
         renderer.exchange_push()
@@ -175,6 +176,7 @@ def composite_final(renderer, rank: int, world: int, dst_rank: int = -1, group=N
     if hkey not in _p2p:
         raise RuntimeError("composite_final needs enable_peer_exchange() to have succeeded")
     token, stream = _p2p[hkey]
+    renderer.readback_wait()
     with torch.cuda.stream(stream):
         dist.all_reduce(token, group=group)
     renderer.exchange_push_final(dst_rank)

@@ -66,6 +66,17 @@ static GkPlane resolvePlane(const Context& c, GkPlane plane)
     }
 }
 
+void waitAsyncCopyBeforeWriting(Context& c, const void* const* buffers, int count)
+{
+    if (!c.asyncCopySrc) return;
+    for (int i = 0; i < count; ++i)
+        if (buffers[i] == c.asyncCopySrc) {
+            cudaStreamWaitEvent(c.stream, c.evCopyDone, 0);
+            c.asyncCopySrc = nullptr; // everything later on the stream is ordered behind the copy
+            return;
+        }
+}
+
 } // namespace gk
 
 using namespace gk;
@@ -158,6 +169,9 @@ void gk_destroy(GkContext* ctx)
     c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release(), c.dRootRef.release();
     c.dCapture.release();
     for (cudaEvent_t e : c.evPool) cudaEventDestroy(e);
+    if (c.evCopyReady) cudaEventDestroy(c.evCopyReady);
+    if (c.evCopyDone) cudaEventDestroy(c.evCopyDone);
+    if (c.copyStream) cudaStreamDestroy(c.copyStream);
     if (c.stream) cudaStreamDestroy(c.stream);
     delete ctx;
 }
@@ -346,6 +360,38 @@ GkStatus gk_readback(GkContext* ctx, GkPlane plane, void* dst, size_t bytes)
     }
     GK_CUDA(cudaMemcpyAsync(dst, c.planes.p[resolvePlane(c, plane)], bytes, cudaMemcpyDeviceToHost, c.stream));
     GK_CUDA(cudaStreamSynchronize(c.stream));
+    return GK_OK;
+}
+
+GkStatus gk_readback_async(GkContext* ctx, GkPlane plane, void* dst, size_t bytes)
+{
+    GK_CHECK_CTX(ctx);
+    if (plane < 0 || plane >= GK_PLANE_COUNT || !dst || bytes != c.planes.bytes[plane]) {
+        setLastError("gk_readback_async: bad plane or size");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    if (!c.copyStream) {
+        GK_CUDA(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+        GK_CUDA(cudaEventCreateWithFlags(&c.evCopyReady, cudaEventDisableTiming));
+        GK_CUDA(cudaEventCreateWithFlags(&c.evCopyDone, cudaEventDisableTiming));
+    }
+    if (c.asyncCopySrc) GK_CUDA(cudaEventSynchronize(c.evCopyDone)); // one copy in flight
+    const void* src = c.planes.p[resolvePlane(c, plane)];
+    GK_CUDA(cudaEventRecord(c.evCopyReady, c.stream));
+    GK_CUDA(cudaStreamWaitEvent(c.copyStream, c.evCopyReady, 0));
+    GK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.copyStream));
+    GK_CUDA(cudaEventRecord(c.evCopyDone, c.copyStream));
+    c.asyncCopySrc = src;
+    return GK_OK;
+}
+
+GkStatus gk_readback_wait(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    if (c.asyncCopySrc) {
+        GK_CUDA(cudaEventSynchronize(c.evCopyDone));
+        c.asyncCopySrc = nullptr;
+    }
     return GK_OK;
 }
 

@@ -172,6 +172,10 @@ struct Context {
     std::vector<cudaEvent_t> evPool;
     int captureWave = -1;
     PeerExchange peers;
+    // asynchronous read-back (gk_readback_async): copy stream + the buffer it is still reading
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evCopyReady = nullptr, evCopyDone = nullptr;
+    const void* asyncCopySrc = nullptr; // non-null while a copy may be in flight
     float tlasAreaAtBuild = 0.f;    // summed internal-node area of the TLAS when it was last built
     uint32_t refitRejected = 0;     // refits that degraded the tree too much and became rebuilds
     DevBuf<uint32_t> dRootRef;
@@ -211,6 +215,7 @@ GkStatus exchangePack(Context& c, void* dStaging);
 GkStatus exchangeUnpack(Context& c, const void* dAll);
 GkStatus exchangeIpcHandles(Context& c, void* out, size_t bytes);
 GkStatus exchangeOpenPeers(Context& c, const void* handlesAll, uint32_t world);
+void waitAsyncCopyBeforeWriting(Context& c, const void* const* buffers, int count); // orders the stream after an in-flight read-back of any of them
 GkStatus exchangePush(Context& c);
 GkStatus exchangePushFinal(Context& c, int dstRank);
 GkStatus filterFrameOwnedRows(Context& c);

@@ -379,6 +379,10 @@ static GkStatus runFilters(Context& c, bool ownedRowsOnly)
     }
     cudaStream_t st = c.stream;
     if (!c.tracedSinceFilter) applyPendingHistorySwap(c); // filter-only use: each call is a new frame
+    {
+        const void* bufs[] = {c.planes.p[GK_PLANE_ACCUM_DIFFUSE], c.planes.p[GK_PLANE_ACCUM_SPECULAR], c.planes.p[GK_PLANE_ACCUM_ALBEDO], c.planes.p[GK_PLANE_DENOISED]};
+        waitAsyncCopyBeforeWriting(c, bufs, 4);
+    }
     c.tracedSinceFilter = false;
     GK_CUDA(cudaMemcpyAsync(c.dUbo, &c.ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, st));
     cudaEvent_t e0, e1, e2;

@@ -725,6 +725,7 @@ template <class T> static cudaError_t allocInto(std::vector<void*>& pool, T*& p,
 
 void freeFrameResources(Context& c)
 {
+    if (c.asyncCopySrc) cudaEventSynchronize(c.evCopyDone), c.asyncCopySrc = nullptr;
     exchangeClosePeers(c); // the mapped peer planes belong to the extent being torn down
     c.peers.myId0 = c.peers.myId1 = nullptr;
     for (void* p : c.pathAllocs) cudaFree(p);
@@ -847,6 +848,13 @@ GkStatus traceFrame(Context& c)
     }
     cudaStream_t st = c.stream;
     applyPendingHistorySwap(c);
+    {
+        static const GkPlane written[] = {GK_PLANE_OUTPUT_DIFFUSE, GK_PLANE_OUTPUT_SPECULAR, GK_PLANE_ALBEDO, GK_PLANE_NORMAL, GK_PLANE_OBJECT_ID0, GK_PLANE_MOTION, GK_PLANE_DEPTH,
+                                          GK_PLANE_RADIANCE_DIFFUSE_F32, GK_PLANE_RADIANCE_SPECULAR_F32, GK_PLANE_PRIMARY_IDS, GK_PLANE_PRIMARY_T, GK_PLANE_RAY_COUNT};
+        const void* bufs[sizeof(written) / sizeof(written[0])];
+        for (size_t i = 0; i < sizeof(written) / sizeof(written[0]); ++i) bufs[i] = c.planes.p[written[i]];
+        waitAsyncCopyBeforeWriting(c, bufs, (int)(sizeof(written) / sizeof(written[0])));
+    }
     c.tracedSinceFilter = true;
     const uint32_t n = c.pathCount;
     FrameParams P{c.width, c.height, c.tileIndex, c.tileCount, c.tileRows, n};

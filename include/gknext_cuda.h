@@ -164,6 +164,12 @@ GkStatus gk_intersect_device(GkContext* ctx, const void* d_rays, uint32_t count,
 size_t gk_plane_bytes(const GkContext* ctx, GkPlane plane);
 GkStatus gk_readback(GkContext* ctx, GkPlane plane, void* dst, size_t bytes);
 GkStatus gk_upload_plane(GkContext* ctx, GkPlane plane, const void* src, size_t bytes);
+/* Read-back that overlaps the next frame: the copy is queued on a second stream behind the work
+ * submitted so far and the call returns at once; `dst` should be page-locked (gk_host_alloc).
+ * Kernels of later frames that overwrite the plane wait for the copy on the device.  One copy can be
+ * in flight per context; gk_readback_wait blocks until `dst` is complete. */
+GkStatus gk_readback_async(GkContext* ctx, GkPlane plane, void* dst, size_t bytes);
+GkStatus gk_readback_wait(GkContext* ctx);
 void* gk_plane_device(GkContext* ctx, GkPlane plane);
 
 /* Frame-end exchange of the tile-partitioned frame (multi-GPU compositor).  gk_exchange_pack

@@ -453,3 +453,32 @@ def test_two_gpu_tile_frame_equals_single_gpu_frame(built):
                               os.path.join(root, "tools", "multi_gpu_check.py")], env=env, capture_output=True, text=True, timeout=300)
         print(out.stdout[-2000:])
         assert out.returncode == 0 and "MULTI_GPU_CHECK PASS" in out.stdout, out.stderr[-2000:]
+
+
+def test_async_readback_overlaps_next_frame_and_returns_the_right_frame(built):
+    """gk_readback_async queues the copy behind frame f; frame f+1 (which overwrites rtDenoised) is
+    submitted before waiting.  The host buffer must hold frame f."""
+    import ctypes as C
+    W, H = 320, 180
+    eng, r, _, _ = _setup("cornell", W, H, (), NumberOfSamples=2, NumberOfBounces=3, Denoiser=1, TemporalFrames=4)
+    lib = gk.cuda_lib()
+    nbytes = r.plane_bytes("DENOISED")
+    pinned = lib.gk_host_alloc(nbytes)
+    assert pinned
+    try:
+        expect = []
+        for frame in range(3):
+            r.set_ubo(eng.ubo(W, H)); r.render_frame(); eng.advance_frame()
+            expect.append(r.readback("DENOISED").view(np.uint16).copy())
+        eng2, r2, _, _ = _setup("cornell", W, H, (), NumberOfSamples=2, NumberOfBounces=3, Denoiser=1, TemporalFrames=4)
+        host = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_uint16)), shape=(H, W, 4))
+        for frame in range(3):
+            r2.set_ubo(eng2.ubo(W, H)); r2.render_frame(); eng2.advance_frame()
+            if frame > 0:
+                r2.readback_wait()  # frame-1's copy, queued before this frame was submitted
+                assert np.array_equal(host, expect[frame - 1]), f"async read-back of frame {frame - 1} differs"
+            r2.readback_async("DENOISED", pinned, nbytes)
+        r2.readback_wait()
+        assert np.array_equal(host, expect[2])
+    finally:
+        lib.gk_host_free(pinned)
