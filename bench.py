@@ -264,10 +264,10 @@ def main():
     info = r.bvh_info()
 
     # ---- timed: device-resident inputs
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # started before the barrier: NVML start-up must not delay rank 0 inside the timed region
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = dict(rays=0, launches=0, ext=0.0, shd=0.0, shade=0.0, gen=0.0, acc=0.0, rep=0.0, jbf=0.0, bvh=0.0, eray=0, sray=0, pray=0, waves=0, tail=0.0, tail_eray=0, tail_paths=0, ext_launches=0)
+    agg = dict(rays=0, launches=0, ext=0.0, shd=0.0, shade=0.0, gen=0.0, acc=0.0, rep=0.0, jbf=0.0, bvh=0.0, eray=0, sray=0, pray=0, waves=0, tail=0.0, tail_eray=0, tail_paths=0, ext_launches=0, trace=0.0)
     xchg_events.clear()
     e0.record(stream)
     t_wall = time.perf_counter()
@@ -277,6 +277,7 @@ def main():
         agg["ext"] += st.msExtend; agg["shd"] += st.msShadow; agg["shade"] += st.msShade; agg["gen"] += st.msGenerate; agg["acc"] += st.msAccumulate
         agg["rep"] += st.msReproject; agg["jbf"] += st.msDenoise; agg["bvh"] += st.msBvh if dynamic else 0.0
         agg["eray"] += st.extensionRays; agg["sray"] += st.shadowRays; agg["pray"] += st.primaryRays; agg["waves"] += st.waves
+        agg["trace"] += st.msTotal
         agg["tail"] += st.msTail; agg["tail_eray"] += st.tailExtensionRays; agg["tail_paths"] += st.tailPaths; agg["ext_launches"] += st.waves - (1 if st.tailPaths else 0)
     e1.record(stream)
     barrier()
@@ -318,7 +319,13 @@ def main():
         c = torch.tensor([agg["rays"], rays_e2e, agg["launches"]], device="cuda", dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         total_rays, total_rays_e2e, total_launches = float(c[0]), float(c[1]), int(c[2])
+        # load balance evidence: device time of the path tracer (generate .. accumulate) and rays per rank and step
+        mine = torch.tensor([agg["trace"] / args.steps, agg["rays"] / args.steps], device="cuda", dtype=torch.float64)
+        every = torch.empty(2 * world, device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(every, mine)
+        per_rank = {"trace_ms": [round(float(v), 3) for v in every[0::2]], "rays": [int(v) for v in every[1::2]]}
     else:
+        per_rank = None
         total_rays, total_rays_e2e, total_launches = float(agg["rays"]), float(rays_e2e), int(agg["launches"])
 
     if world > 1:
@@ -389,6 +396,7 @@ def main():
         "e2e": {"value": round(total_rays_e2e / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "api": "CudaPathTracingRenderer::BeforeNextFrame + Render (host mirror of LogicRendererBase) + gk_readback_async(rtDenoised) to pinned memory, double-buffered"},
         "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "shade", "tail", "acc", "xchg", "rep", "jbf", "bvh")},
+        "per_rank": per_rank,
         "tail_paths_per_step": round(agg["tail_paths"] / args.steps, 0),
         "host_gap_ms_per_step": round((wall_ms - dev_ms) / args.steps, 4),
         "bvh": {"blas_build_ms": round(info.msBlasBuild, 3), "tlas_build_ms": round(info.msTlasBuild, 3), "tlas_refit_ms": round(info.msRefit, 3), "refits_rejected": int(r.bvh_info().refitsRejected),

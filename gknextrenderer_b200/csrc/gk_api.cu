@@ -135,6 +135,8 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     // measured on the 1080p room (sweep 16 K .. 4 M paths): the one-launch tail wins below ~2.5-3.5 K paths per SM (1 and 2 GPUs)
     c.tailThreshold = 3584u * (uint32_t)prop.multiProcessorCount;
     if (const char* e = getenv("GK_BLAS_LEAF")) c.blasLeafMax = (uint32_t)std::min(8, std::max(1, atoi(e)));
+    if (const char* e = getenv("GK_CONCURRENT_SHADOW")) c.concurrentShadow = atoi(e) != 0;
+    if (const char* e = getenv("GK_TRACE_BLOCK")) c.laneBlock = (unsigned)std::min(256, std::max(32, atoi(e) / 32 * 32));
     if (const char* e = getenv("GK_SHADE_BLOCKS")) c.shadeMinBlocks = atoi(e);
     if (const char* e = getenv("GK_SAH_COLLAPSE")) c.sahCollapse = atoi(e) != 0;
     if (const char* e = getenv("GK_TAIL_FRACTION")) c.tailFraction = (float)atof(e);
@@ -169,6 +171,9 @@ void gk_destroy(GkContext* ctx)
     c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release(), c.dRootRef.release();
     c.dCapture.release();
     for (cudaEvent_t e : c.evPool) cudaEventDestroy(e);
+    if (c.evFork) cudaEventDestroy(c.evFork);
+    if (c.evJoin) cudaEventDestroy(c.evJoin);
+    if (c.stream2) cudaStreamDestroy(c.stream2);
     if (c.evCopyReady) cudaEventDestroy(c.evCopyReady);
     if (c.evCopyDone) cudaEventDestroy(c.evCopyDone);
     if (c.copyStream) cudaStreamDestroy(c.copyStream);

@@ -179,6 +179,10 @@ struct Context {
     float tlasAreaAtBuild = 0.f;    // summed internal-node area of the TLAS when it was last built
     uint32_t refitRejected = 0;     // refits that degraded the tree too much and became rebuilds
     DevBuf<uint32_t> dRootRef;
+    bool concurrentShadow = true;   // shadow kernel of a wave on a second stream, next to the extend kernel
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    unsigned laneBlock = 256;       // threads (= rays) per block of the one-ray-per-lane trace kernel
     int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
     bool sahCollapse = true;        // cost-driven wide collapse (false: greedy by surface area)
     DevBuf<float4> dCapture;

@@ -685,28 +685,29 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams P, PathState S, 
 
 // -------------------------------------------------------------------------------- utilities
 template <bool kAnyHit, bool kCoop, class RayIO>
-static void launchMapped(cudaStream_t st, unsigned grid, const SceneView& V, const RayIO& io, uint32_t count, TraversalStats* ts)
+static void launchMapped(cudaStream_t st, unsigned grid, unsigned block, const SceneView& V, const RayIO& io, uint32_t count, TraversalStats* ts)
 {
-    if (ts) k_trace<kAnyHit, kCoop, true, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
-    else k_trace<kAnyHit, kCoop, false, RayIO><<<grid, 256, 0, st>>>(V, io, count, ts);
+    if (ts) k_trace<kAnyHit, kCoop, true, RayIO><<<grid, block, 0, st>>>(V, io, count, ts);
+    else k_trace<kAnyHit, kCoop, false, RayIO><<<grid, block, 0, st>>>(V, io, count, ts);
 }
 
 template <bool kAnyHit, class RayIO>
-static void launchTraceIO(Context& c, const SceneView& V, const RayIO& io, uint32_t count)
+static void launchTraceIO(Context& c, const SceneView& V, const RayIO& io, uint32_t count, cudaStream_t stream = nullptr)
 {
+    if (!stream) stream = c.stream;
     const bool coop = count < c.coopThreshold;
-    const unsigned per = coop ? kRaysPerBlock : 256;
+    const unsigned per = coop ? kRaysPerBlock : c.laneBlock; // rays per block
     const unsigned grid = (count + per - 1) / per;
     TraversalStats* ts = c.travStats ? c.dTravStats : nullptr;
-    if (coop) launchMapped<kAnyHit, true>(c.stream, grid, V, io, count, ts);
-    else launchMapped<kAnyHit, false>(c.stream, grid, V, io, count, ts);
+    if (coop) launchMapped<kAnyHit, true>(stream, grid, 256, V, io, count, ts);
+    else launchMapped<kAnyHit, false>(stream, grid, c.laneBlock, V, io, count, ts);
 }
 
 template <bool kShadow>
-static void launchTrace(Context& c, const SceneView& V, const RayQueue& Q, uint32_t count)
+static void launchTrace(Context& c, const SceneView& V, const RayQueue& Q, uint32_t count, cudaStream_t stream = nullptr)
 {
-    if (kShadow) launchTraceIO<true>(c, V, ShadowIO{Q}, count);
-    else launchTraceIO<false>(c, V, QueueIO{Q}, count);
+    if (kShadow) launchTraceIO<true>(c, V, ShadowIO{Q}, count, stream);
+    else launchTraceIO<false>(c, V, QueueIO{Q}, count, stream);
 }
 
 // -------------------------------------------------------------------------------- host side
@@ -869,6 +870,12 @@ GkStatus traceFrame(Context& c)
     struct Span { size_t a, b; int kind; };
     std::vector<Span> spans;
     auto mark = [&]() { cudaEvent_t e = poolEvent(c, ev); cudaEventRecord(e, st); return ev++; };
+    auto markOn = [&](cudaStream_t s) { cudaEvent_t e = poolEvent(c, ev); cudaEventRecord(e, s); return ev++; };
+    if (c.concurrentShadow && !c.stream2) {
+        GK_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+        GK_CUDA(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
+        GK_CUDA(cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming));
+    }
 
     GK_CUDA(cudaMemcpyAsync(c.dUbo, &c.ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, st));
     if (c.travStats) GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), st));
@@ -912,15 +919,35 @@ GkStatus traceFrame(Context& c)
                 GK_CUDA(cudaMemcpy2DAsync(c.dCapture.p + 1, 32, c.extendQ[cur].d_tmax, 16, 16, countE, cudaMemcpyDeviceToDevice, st));
                 c.capturedCount = countE;
             }
+        }
+        // extend and shadow rays of a wave are independent: the shadow kernel runs on a second stream so
+        // that its blocks fill the SMs the long tail of the extend kernel leaves idle (and vice versa)
+        const bool fork = countE && countS && c.concurrentShadow;
+        size_t b, d, s0 = 0, s1 = 0;
+        if (fork) {
+            GK_CUDA(cudaEventRecord(c.evFork, st));
+            GK_CUDA(cudaStreamWaitEvent(c.stream2, c.evFork, 0));
+            s0 = markOn(c.stream2);
+            launchTrace<true>(c, V, c.shadowQ[cur], countS, c.stream2);
+            s1 = markOn(c.stream2);
+            GK_CUDA(cudaEventRecord(c.evJoin, c.stream2));
             launchTrace<false>(c, V, c.extendQ[cur], countE);
-            fs.launches++;
+            b = mark();
+            GK_CUDA(cudaStreamWaitEvent(st, c.evJoin, 0));
+            d = mark();
+            fs.launches += 2;
+        } else {
+            if (countE) {
+                launchTrace<false>(c, V, c.extendQ[cur], countE);
+                fs.launches++;
+            }
+            b = mark();
+            if (countS) {
+                launchTrace<true>(c, V, c.shadowQ[cur], countS);
+                fs.launches++;
+            }
+            d = mark();
         }
-        const size_t b = mark();
-        if (countS) {
-            launchTrace<true>(c, V, c.shadowQ[cur], countS);
-            fs.launches++;
-        }
-        const size_t d = mark();
         const int nxt = cur ^ 1;
         GK_CUDA(cudaMemsetAsync(c.extendQ[nxt].count, 0, sizeof(uint32_t), st));
         GK_CUDA(cudaMemsetAsync(c.shadowQ[nxt].count, 0, sizeof(uint32_t), st));
@@ -932,7 +959,9 @@ GkStatus traceFrame(Context& c)
                                                                      c.shadowQ[nxt]);
         fs.launches++;
         const size_t f = mark();
-        spans.push_back({a, b, 1}), spans.push_back({b, d, 2}), spans.push_back({d, f, 3});
+        spans.push_back({a, b, 1}), spans.push_back({d, f, 3});
+        if (fork) spans.push_back({s0, s1, 2}); // overlaps the extend span
+        else spans.push_back({b, d, 2});
         GK_CUDA(cudaMemcpyAsync(c.hCounts, c.extendQ[nxt].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaMemcpyAsync(c.hCounts + 1, c.shadowQ[nxt].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaStreamSynchronize(st));

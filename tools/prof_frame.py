@@ -23,7 +23,8 @@ def main():
     scene, args, W, H, settings = WORKLOADS[name]
     eng = gk.Engine(scene, *args)
     eng.set(**settings)
-    r = gk.Renderer(W, H, device=0)
+    tiles = int(os.environ.get("GK_PROF_TILES", "1"))  # >1: the per-rank share of a tile-partitioned frame
+    r = gk.Renderer(W, H, device=0, tile_index=0, tile_count=tiles, tile_rows=16)
     r.load(eng)
     cudart = ctypes.CDLL(None)  # libcudart is already in the process (pulled in by libgknext_cuda.so, RTLD_GLOBAL)
     for f in range(3):
