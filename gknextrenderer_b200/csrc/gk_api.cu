@@ -495,7 +495,7 @@ GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out)
     if (c.travStats) {
         TraversalStats h;
         GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));
-        c.stats.nodeVisits = h.nodeVisits, c.stats.triTests = h.triTests, c.stats.tlasVisits = h.tlasVisits, c.stats.instanceEntries = h.instanceEntries;
+        c.stats.nodeVisits = h.nodeVisits, c.stats.triTests = h.triTests, c.stats.tlasVisits = h.tlasVisits, c.stats.instanceEntries = h.instanceEntries, c.stats.maxStack = (uint32_t)h.maxStack;
     }
     *out = c.stats;
     return GK_OK;

@@ -95,6 +95,7 @@ struct Hit {
 
 struct TraversalStats {
     unsigned long long nodeVisits, triTests, tlasVisits, instanceEntries;
+    unsigned long long maxStack; // deepest traversal stack seen (entries); must stay below kStackSize
 };
 
 // ---- exact triangle test -------------------------------------------------------------
@@ -233,6 +234,10 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
                     const int rank = __popc(others & ((1u << sub) - 1u));
                     if (rank < room) stackRow[sp + rank] = make_uint2(ref, __float_as_uint(tn));
                 }
+                if (kStats && sub == 0) {
+                    if (__popc(others) > room) stats->maxStack = kStackSize + 1;
+                    else if ((unsigned long long)(sp + __popc(others)) > stats->maxStack) stats->maxStack = sp + __popc(others);
+                }
                 sp += min(__popc(others), room);
                 cur = __shfl_sync(gmask, ref, near + shift);
                 continue;
@@ -367,9 +372,11 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
                         float pt = tn;
                         if (tn < bestT) { pr = bestRef, pt = bestT, bestRef = ref, bestT = tn; }
                         if (pr != kInvalid && sp < kStackSize) stk.e[sp++] = make_uint2(pr, __float_as_uint(pt));
+                        else if (kStats && pr != kInvalid) stats->maxStack = kStackSize + 1; // an entry was dropped
                     }
                 }
             }
+            if (kStats && (unsigned long long)sp > stats->maxStack) stats->maxStack = sp;
             if (bestRef != kInvalid) cur = bestRef;
             else { GK_POP() }
         }

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(256, kCoop ? 2 : 4) k_trace(SceneView V, RayIO
             atomicAdd(&stats->triTests, local.triTests);
             atomicAdd(&stats->tlasVisits, local.tlasVisits);
             atomicAdd(&stats->instanceEntries, local.instanceEntries);
+            atomicMax(&stats->maxStack, local.maxStack);
         }
     }
 }
@@ -998,7 +999,7 @@ GkStatus traceFrame(Context& c)
     if (c.travStats) {
         TraversalStats h;
         GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));
-        fs.nodeVisits = h.nodeVisits, fs.triTests = h.triTests, fs.tlasVisits = h.tlasVisits, fs.instanceEntries = h.instanceEntries;
+        fs.nodeVisits = h.nodeVisits, fs.triTests = h.triTests, fs.tlasVisits = h.tlasVisits, fs.instanceEntries = h.instanceEntries, fs.maxStack = (uint32_t)h.maxStack;
     }
     return GK_OK;
 }

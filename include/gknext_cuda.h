@@ -27,6 +27,7 @@ extern "C" {
 #endif
 
 #define GK_ABI_VERSION 1
+#define GK_TRAVERSAL_STACK 48 /* entries of the per-ray traversal stack */
 
 typedef enum GkStatus {
     GK_OK = 0,
@@ -96,6 +97,8 @@ typedef struct GkFrameStats {
     float msTail;       /* the single launch that finishes the last paths of the frame */
     uint32_t tailPaths; /* paths alive when that launch started */
     uint64_t tailExtensionRays, tailShadowRays; /* part of extensionRays / shadowRays traced by that launch */
+    uint32_t maxStack;  /* traversal statistics: deepest stack seen; GK_TRAVERSAL_STACK + 1 means an entry was dropped */
+    uint32_t reserved0;
 } GkFrameStats;
 
 typedef struct GkBvhInfo {

@@ -482,3 +482,18 @@ def test_async_readback_overlaps_next_frame_and_returns_the_right_frame(built):
         assert np.array_equal(host, expect[2])
     finally:
         lib.gk_host_free(pinned)
+
+
+@pytest.mark.parametrize("scene,args", [("room", (200000, 3)), ("bricks", (20000, 42)), ("city", (8, 20, 7, 12)), ("cornell", ())])
+def test_traversal_stack_never_overflows(built, scene, args):
+    """The per-ray stack has GK_TRAVERSAL_STACK (48) entries; a dropped entry would be a silently missed hit.
+    The instrumented traversal reports the deepest stack of a whole frame (both ray-to-lane mappings run)."""
+    W, H = 480, 270
+    eng, r, _, _ = _setup(scene, W, H, args, NumberOfSamples=1, NumberOfBounces=4)
+    r.set_traversal_stats(True)
+    r.set_ubo(eng.ubo(W, H))
+    r.trace_frame()
+    st = r.stats()
+    rays = st.primaryRays + st.extensionRays + st.shadowRays
+    print(f"[{scene}] rays {rays} deepest stack {st.maxStack} of 48, node visits/ray {st.nodeVisits / rays:.1f}")
+    assert 0 < st.maxStack <= 48
