@@ -168,6 +168,13 @@ class Renderer:
         nodes, n = engine.update_nodes()
         self.update_instances(nodes, n, refit)
 
+    def set_probes(self, cubes: np.ndarray, voxels: np.ndarray):
+        """Ambient-cube grid (192 x 48 x 192 probes): cubes (N, 14) uint32, voxels (N, 4) uint32."""
+        cubes = np.ascontiguousarray(cubes, np.uint32)
+        voxels = np.ascontiguousarray(voxels, np.uint32)
+        assert cubes.shape[1] == 14 and voxels.shape[1] == 4 and cubes.shape[0] == voxels.shape[0]
+        self._check(self.lib.gk_set_probes(self.h, cubes.ctypes.data_as(C.c_void_p), voxels.ctypes.data_as(C.c_void_p), cubes.shape[0]))
+
     def set_ubo(self, ubo):
         self._check(self.lib.gk_set_ubo(self.h, C.byref(ubo)))
 

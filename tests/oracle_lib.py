@@ -137,7 +137,7 @@ class OracleScene:
         # number of models is not exported; probe until the caller-supplied count
         return pre, out, m
 
-    def render(self, ubo, width, height, threads=8):
+    def render(self, ubo, width, height, threads=8, cubes=None, voxels=None):
         px = width * height
         o = {
             "diffuse": np.zeros((height, width, 4), np.float32), "spec": np.zeros((height, width, 4), np.float32),
@@ -147,7 +147,8 @@ class OracleScene:
             "rayCount": np.zeros((height, width), np.uint32),
         }
         assert px == o["depth"].size
-        self.lib.orc_render(self.h, C.cast(C.byref(ubo), _P), width, height, None, None, ptr(o["diffuse"]), ptr(o["spec"]), ptr(o["albedo"]),
+        self.lib.orc_render(self.h, C.cast(C.byref(ubo), _P), width, height, ptr(cubes) if cubes is not None else None,
+                            ptr(voxels) if voxels is not None else None, ptr(o["diffuse"]), ptr(o["spec"]), ptr(o["albedo"]),
                             ptr(o["normal"]), ptr(o["motion"]), ptr(o["depth"]), ptr(o["objectId"]), ptr(o["primIds"]), ptr(o["rayCount"]), threads)
         return o
 
