@@ -521,3 +521,80 @@ def test_ambient_cube_terminator_with_baked_probes(built):
     # the probe term must actually contribute: compare against the un-baked frame of the oracle
     o0 = orc.render(ubo, W, H, threads=os.cpu_count() or 1)
     assert float(np.abs(o["diffuse"][..., :3] - o0["diffuse"][..., :3]).mean()) > 1e-3
+
+
+# ---------------------------------------------------------------- edge cases of the boundary
+def _proxy_copy(nodes, n):
+    import ctypes as C
+    arr = (gk.GkNodeProxy * n)()
+    C.memmove(arr, nodes, n * C.sizeof(gk.GkNodeProxy))
+    return arr
+
+
+def test_hidden_and_nort_instances_are_skipped(built):
+    """TLAS instances exist only for nodes with visible && !nort (RayTraceBaseRenderer.cpp:188-189); the
+    proxy list keeps its length, so instance ids of the remaining nodes must not shift."""
+    eng, r, orc, (nodes, n) = _setup("cornell", 64, 64)
+    rng = np.random.default_rng(3)
+    rays = _random_rays(rng, 60000, (-2.5, 0.2, -2.5), (2.5, 5.0, 2.5))
+    for hide, field in ((1, "visible"), (2, "nort"), (None, None)):
+        arr = _proxy_copy(nodes, n)
+        if hide is not None:
+            setattr(arr[hide], field, 0 if field == "visible" else 1)
+        r.update_instances(arr, n)
+        orc.set_nodes(arr, n)
+        _compare_hits(r, orc, rays, f"cornell with node {hide} {field}", max_tie_fraction=5e-3)  # the tall box stands on the floor: coplanar faces
+        _, ids = r.intersect(rays)
+        hit = ids[:, 1] != 0xFFFFFFFF
+        if hide is not None:
+            assert not (ids[hit, 1] == hide).any()
+        assert set(np.unique(ids[hit, 1])) <= set(range(n))
+    # every instance hidden: all rays miss, a frame is all sky and traces only the primary rays
+    arr = _proxy_copy(nodes, n)
+    for i in range(n):
+        arr[i].visible = 0
+    r.update_instances(arr, n)
+    tuv, ids = r.intersect(rays)
+    assert (ids == 0xFFFFFFFF).all()
+    W = H = 64
+    r.set_ubo(eng.ubo(W, H))
+    r.render_frame()
+    st = r.stats()
+    assert st.primaryRays == W * H and st.extensionRays == 0 and st.shadowRays == 0
+    assert (r.readback("OBJECT_ID0") == 65535).all()
+
+
+def test_api_misuse_fails_loudly(built):
+    """Error convention of the C ABI: negative status + gk_last_error text, never a crash or a silent no-op."""
+    r = gk.Renderer(32, 32, device=0)
+    with pytest.raises(gk.GkError) as e:
+        r.render_frame()  # nothing uploaded
+    assert e.value.status == -4 and "must be set" in str(e.value)
+    eng = gk.Engine("cornell")
+    with pytest.raises(gk.GkError):
+        nodes, n = eng.update_nodes()
+        r.update_instances(nodes, n)  # instances before the scene
+    r.upload_scene(eng.scene_desc())
+    nodes, n = eng.update_nodes()
+    with pytest.raises(gk.GkError) as e:
+        r.update_instances(nodes, 0)
+    assert e.value.status == -1
+    r.update_instances(nodes, n)
+    with pytest.raises(gk.GkError):
+        r.render_frame()  # no UBO yet
+    r.set_ubo(eng.ubo(32, 32))
+    r.render_frame()
+    with pytest.raises(AssertionError):
+        r.readback("DENOISED", np.empty((16, 16, 4), np.float16))  # wrapper checks the size ...
+    import ctypes as C
+    buf = np.empty(16, np.uint8)
+    assert r.lib.gk_readback(r.h, gk.PLANES["DENOISED"], buf.ctypes.data_as(C.c_void_p), buf.nbytes) == -1  # ... and so does the ABI
+    assert b"size" in r.lib.gk_last_error()
+    with pytest.raises(gk.GkError):
+        gk.Renderer(32, 32, device=0, tile_index=3, tile_count=2)
+    # resize keeps the scene and produces a frame of the new extent
+    r._check(r.lib.gk_resize(r.h, 48, 40))
+    r.width, r.height = 48, 40
+    r.set_ubo(eng.ubo(48, 40))
+    r.render_frame()
+    assert r.readback("DENOISED").shape == (40, 48, 4)
