@@ -90,7 +90,8 @@ __device__ __forceinline__ unsigned long long spread14(uint32_t v)
 }
 
 __global__ void k_morton(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ group, uint32_t n,
-                         const float4* __restrict__ glo, const float4* __restrict__ ghi, unsigned long long* __restrict__ keys, uint32_t* __restrict__ order)
+                         const float4* __restrict__ glo, const float4* __restrict__ ghi, unsigned long long* __restrict__ keys, uint32_t* __restrict__ order,
+                         int sizeBits)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -106,8 +107,25 @@ __global__ void k_morton(const float4* __restrict__ plo, const float4* __restric
     }
     const uint32_t qx = min(16383u, (uint32_t)(fmaxf(cx, 0.f) * 16384.f)), qy = min(16383u, (uint32_t)(fmaxf(cy, 0.f) * 16384.f)),
                    qz = min(16383u, (uint32_t)(fmaxf(cz, 0.f) * 16384.f));
-    const unsigned long long m = (spread14(qx) << 2) | (spread14(qy) << 1) | spread14(qz);
-    keys[i] = ((unsigned long long)g << 42) | m;
+    unsigned long long m = (spread14(qx) << 2) | (spread14(qy) << 1) | spread14(qz);
+    if (sizeBits > 0 && a.x <= b.x) {
+        // extended Morton code (Vinkler et al. 2017): bits of the box size are woven in between the position
+        // bits (one before every second x/y/z triple), so that boxes much larger than their neighbours
+        // split off near the top of the tree instead of bloating every level below
+        const float ex = gh.x - gl.x, ey = gh.y - gl.y, ez = gh.z - gl.z;
+        const float gd = sqrtf(ex * ex + ey * ey + ez * ez);
+        const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+        const float rel = gd > 0 ? sqrtf(dx * dx + dy * dy + dz * dz) / gd : 0.f;
+        const uint32_t s = min((1u << sizeBits) - 1u, (uint32_t)(fminf(rel, 1.f) * (float)(1u << sizeBits)));
+        unsigned long long e = 0;
+        int sb = sizeBits - 1;
+        for (int t = 0; t < 14; ++t) { // from the most significant triple down
+            if ((t & 1) == 0 && sb >= 0) e = (e << 1) | ((s >> sb--) & 1u);
+            e = (e << 3) | ((m >> (3 * (13 - t))) & 7ull);
+        }
+        m = e;
+    }
+    keys[i] = ((unsigned long long)g << (42 + max(sizeBits, 0))) | m;
     order[i] = i;
 }
 
@@ -248,18 +266,18 @@ __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left
 
 // ------------------------------------------------------------------ per-group roots
 __global__ void k_group_roots(const unsigned long long* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
-                              uint32_t* __restrict__ groupRoot)
+                              uint32_t* __restrict__ groupRoot, int groupShift)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { // single-primitive groups: the leaf is the root
-        const unsigned long long g = keys[i] >> 42;
-        const bool lonelyL = (i == 0) || (keys[i - 1] >> 42) != g, lonelyR = (i == n - 1) || (keys[i + 1] >> 42) != g;
+        const unsigned long long g = keys[i] >> groupShift;
+        const bool lonelyL = (i == 0) || (keys[i - 1] >> groupShift) != g, lonelyR = (i == n - 1) || (keys[i + 1] >> groupShift) != g;
         if (lonelyL && lonelyR) groupRoot[g] = kLeafBit | i;
     }
     if (i + 1 < n) {
         const uint32_t a = first[i], b = last[i];
-        const unsigned long long g = keys[a] >> 42;
-        if ((keys[b] >> 42) == g && (a == 0 || (keys[a - 1] >> 42) != g) && (b == n - 1 || (keys[b + 1] >> 42) != g)) groupRoot[g] = i;
+        const unsigned long long g = keys[a] >> groupShift;
+        if ((keys[b] >> groupShift) == g && (a == 0 || (keys[a - 1] >> groupShift) != g) && (b == n - 1 || (keys[b + 1] >> groupShift) != g)) groupRoot[g] = i;
     }
 }
 
@@ -603,7 +621,7 @@ void Lbvh::release()
 static inline unsigned gridFor(size_t n, unsigned block = 256) { return (unsigned)((n + block - 1) / block); }
 
 // Steps 1-5 over T.plo/T.phi/T.group (group may be null => one group).
-static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint32_t groups, int keyBits)
+static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint32_t groups, int keyBits, int sizeBits = 0)
 {
     const uint32_t n = T.n;
     cudaStream_t st = c.stream;
@@ -626,7 +644,7 @@ static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint3
     GK_CUDA(c.dGroupHi.reserve(groups));
     k_init_group_bounds<<<gridFor(groups), 256, 0, st>>>(c.dGroupLo.p, c.dGroupHi.p, groups);
     k_group_bounds<<<gridFor(n), 256, 0, st>>>(T.plo.p, T.phi.p, group, n, c.dGroupLo.p, c.dGroupHi.p);
-    k_morton<<<gridFor(n), 256, 0, st>>>(T.plo.p, T.phi.p, group, n, c.dGroupLo.p, c.dGroupHi.p, T.keysAlt.p, T.orderAlt.p);
+    k_morton<<<gridFor(n), 256, 0, st>>>(T.plo.p, T.phi.p, group, n, c.dGroupLo.p, c.dGroupHi.p, T.keysAlt.p, T.orderAlt.p, sizeBits);
     size_t tempBytes = 0;
     GK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, T.keysAlt.p, T.keys.p, T.orderAlt.p, T.order.p, (int)n, 0, keyBits, st));
     GK_CUDA(c.dSortTemp.reserve(tempBytes));
@@ -666,7 +684,7 @@ static Bvh2View viewOf(const Lbvh& T)
 
 // Step 6+7.  rootRef (device, one per group) receives the wide root reference of each group.
 static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax, bool tlas, DevBuf<WideNode>& nodes, DevBuf<uint32_t>& nodeSrc, uint32_t& nodeCount,
-                         uint32_t* dRootRef)
+                         uint32_t* dRootRef, int groupShift = 42)
 {
     const uint32_t n = T.n;
     cudaStream_t st = c.stream;
@@ -680,7 +698,7 @@ static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax,
     GK_CUDA(cudaMemsetAsync(c.dGroupRoot.p, 0xff, sizeof(uint32_t) * groups, st));
     GK_CUDA(cudaMemsetAsync(c.dCounters.p, 0, sizeof(uint32_t) * 8, st));
     const Bvh2View B = viewOf(T);
-    k_group_roots<<<gridFor(n), 256, 0, st>>>(T.keys.p, n, T.first.p, T.last.p, c.dGroupRoot.p);
+    k_group_roots<<<gridFor(n), 256, 0, st>>>(T.keys.p, n, T.first.p, T.last.p, c.dGroupRoot.p, groupShift);
     k_collapse_seed<<<gridFor(groups), 256, 0, st>>>(B, c.dGroupRoot.p, groups, leafMax, tlas ? 1 : 0, dRootRef, c.dTaskA.p, c.dCounters.p);
     uint32_t* in = c.dTaskA.p;
     uint32_t* out = c.dTaskB.p;
@@ -784,14 +802,14 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
         }
     }
     if (!refit) {
-        s = buildRadixTree(c, T, nullptr, 1, 42);
+        s = buildRadixTree(c, T, nullptr, 1, 42 + c.tlasSizeBits, c.tlasSizeBits);
         if (s != GK_OK) return s;
         GK_CUDA(cudaMemsetAsync(dArea, 0, sizeof(float), st));
         s = propagateBounds(c, T, c.sahCollapse, 0, kCostInstance, dArea);
         if (s != GK_OK) return s;
         GK_CUDA(cudaMemcpyAsync(&c.tlasAreaAtBuild, dArea, sizeof(float), cudaMemcpyDeviceToHost, st));
         GK_CUDA(c.dRootRef.reserve(1));
-        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.dTlasSrc, c.tlasNodeCount, c.dRootRef.p);
+        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.dTlasSrc, c.tlasNodeCount, c.dRootRef.p, 42 + c.tlasSizeBits);
         if (s != GK_OK) return s;
         GK_CUDA(cudaMemcpyAsync(&c.tlasRoot, c.dRootRef.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaStreamSynchronize(st));

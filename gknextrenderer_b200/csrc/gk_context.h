@@ -184,6 +184,7 @@ struct Context {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     unsigned laneBlock = 256;       // threads (= rays) per block of the one-ray-per-lane trace kernel
     int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
+    int tlasSizeBits = 2;           // extended Morton code of the TLAS: box-size bits woven into the key (0 = plain Morton)
     bool sahCollapse = true;        // cost-driven wide collapse (false: greedy by surface area)
     DevBuf<float4> dCapture;
     uint32_t capturedCount = 0;
