@@ -74,8 +74,8 @@ struct __align__(16) InstRecord {
     float invT[16];    // row-major inverse world transform (tinybvh BLASInstance::invTransform)
     uint32_t blasRoot; // reference into the BLAS node array (may be a leaf reference)
     uint32_t node;     // index into the NodeProxy array
-    uint32_t model;
-    uint32_t pad;
+    uint32_t indexOffset;  // first index / first vertex of the instance's model: the shading fetch goes
+    uint32_t vertexOffset; // instance -> indices -> vertices without passing through NodeProxy and ModelInfo
 };
 static_assert(sizeof(InstRecord) == 80, "InstRecord");
 

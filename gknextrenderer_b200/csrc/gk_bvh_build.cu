@@ -583,7 +583,8 @@ __global__ void k_update_instances(const GkNodeProxy* __restrict__ nodes, uint32
 #pragma unroll
         for (int c = 0; c < 4; ++c) T[r * 4 + c] = P.worldTS[c * 4 + r]; // glm column-major -> tinybvh row-major
     invert4x4RowMajor(T, R.invT);
-    R.node = i, R.model = model, R.pad = 0;
+    R.node = i;
+    R.indexOffset = model < modelCount ? models[model].indexOffset : 0u, R.vertexOffset = model < modelCount ? models[model].vertexOffset : 0u;
     R.blasRoot = visible ? models[model].blasRoot : kInvalid;
     float4 lo = make_float4(kFar, kFar, kFar, 0), hi = make_float4(-kFar, -kFar, -kFar, 0);
     if (visible && R.blasRoot != kInvalid) {

@@ -206,7 +206,7 @@ struct Vtx {
 GK_HD Vtx getMaterialData(const ShadeScene& S, uint32_t node, uint32_t prim, f3 ro, f3 rd, uint32_t& rawMat)
 {
     const GkNodeProxy& px = S.nodes[node];
-    const ModelInfo& M = S.models[px.modelId / 10];
+    const InstRecord& M = S.inst[node];
     const float* W = px.worldTS;
     f3 P[3], N[3];
     f2 T[3];
@@ -238,19 +238,18 @@ GK_HD Vtx getMaterialData(const ShadeScene& S, uint32_t node, uint32_t prim, f3 
 // Shading.slang:725-747 — shading vertex of a traced hit.
 GK_HD void resolveHit(const ShadeScene& S, f3 ro, f3 rd, float t, float u, float v, uint32_t prim, uint32_t node, Vtx& out)
 {
-    const GkNodeProxy& px = S.nodes[node];
-    const ModelInfo& M = S.models[px.modelId / 10];
-    const uint32_t* idx = S.indices + M.indexOffset + prim * 3;
-    const UnpackedV v0 = unpackVertex(S.verts, M.vertexOffset + idx[0]);
-    const UnpackedV v1 = unpackVertex(S.verts, M.vertexOffset + idx[1]);
-    const UnpackedV v2 = unpackVertex(S.verts, M.vertexOffset + idx[2]);
+    const InstRecord& I = S.inst[node];
+    const uint32_t* idx = S.indices + I.indexOffset + prim * 3;
+    const UnpackedV v0 = unpackVertex(S.verts, I.vertexOffset + idx[0]);
+    const UnpackedV v1 = unpackVertex(S.verts, I.vertexOffset + idx[1]);
+    const UnpackedV v2 = unpackVertex(S.verts, I.vertexOffset + idx[2]);
     const f3 n = v0.N + (v1.N - v0.N) * u + (v2.N - v0.N) * v;
-    const float* inv = S.inst[node].invT; // row-major inverse world transform
+    const float* inv = I.invT; // row-major inverse world transform
     const f3 nw = mk3(inv[0] * n.x + inv[4] * n.y + inv[8] * n.z, inv[1] * n.x + inv[5] * n.y + inv[9] * n.z, inv[2] * n.x + inv[6] * n.y + inv[10] * n.z);
     out.Normal = normalize3(nw);
     out.TexCoord = f2{v0.uv.x + (v1.uv.x - v0.uv.x) * u + (v2.uv.x - v0.uv.x) * v, v0.uv.y + (v1.uv.y - v0.uv.y) * u + (v2.uv.y - v0.uv.y) * v};
     out.Position = ro + rd * t;
-    out.MaterialIndex = px.matId[v0.mat & 15];
+    out.MaterialIndex = S.nodes[node].matId[v0.mat & 15];
 }
 
 GK_HD f3 skyColor(const GkUniformBufferObject& U) // Shading.slang:148-153 with a constant texel
