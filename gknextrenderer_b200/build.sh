@@ -21,5 +21,5 @@ done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 $NVCC $ARCH -shared -o lib/libgknext_cuda.so "${objs[@]}" -lcudart
 g++ -O2 -std=c++17 -fPIC -shared -Wall -o lib/libgknext_host.so host/gk_assets.cpp host/gk_engine.cpp host/gk_host_capi.cpp \
-    -Llib -lgknext_cuda -Wl,-rpath,'$ORIGIN'
+    -pthread -Llib -lgknext_cuda -Wl,-rpath,'$ORIGIN'
 echo "built lib/libgknext_cuda.so lib/libgknext_host.so"

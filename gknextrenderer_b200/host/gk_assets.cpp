@@ -3,7 +3,9 @@
 #include "../../include/gknext_cuda.h"
 #include <algorithm>
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <random>
 #include <unordered_set>
@@ -267,21 +269,45 @@ bool Scene::UpdateNodes() // Scene.cpp:464-511
 {
     if (nodes_.empty() || !sceneDirty_) return false;
     sceneDirty_ = false;
-    nodeProxys_.clear();
-    for (auto& node : nodes_) {
-        if (!node->IsDrawable()) continue;
-        mat4 combined;
-        if (node->TickVelocity(combined)) MarkDirty();
-        if (node->GetModel() >= models_.size()) continue;
-        const Model& model = models_[node->GetModel()];
-        for (uint32_t section = 0; section < model.SectionCount(); ++section) {
-            nodeProxys_.push_back(node->GetNodeProxy());
-            NodeProxy& proxy = nodeProxys_.back();
-            memcpy(proxy.combinedPrevTS, combined.data(), 64);
-            proxy.modelId = node->GetModel() * 10 + section;
-            proxy.nort = section == 0 ? 0 : 1;
-        }
+    // The proxy of a node depends on that node only, so large scenes are filled by several threads:
+    // pass 1 counts the proxies of every node (drawable, valid model, one per section), pass 2 writes
+    // them at their prefix offsets.  The result is identical to the sequential loop of the reference.
+    const size_t n = nodes_.size();
+    std::vector<uint32_t> offset(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) {
+        const auto& node = nodes_[i];
+        uint32_t c = 0;
+        if (node->IsDrawable() && node->GetModel() < models_.size()) c = models_[node->GetModel()].SectionCount();
+        offset[i + 1] = offset[i] + c;
     }
+    nodeProxys_.resize(offset[n]);
+    std::atomic<bool> moved{false};
+    auto fill = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            auto& node = nodes_[i];
+            if (!node->IsDrawable()) continue;
+            mat4 combined;
+            if (node->TickVelocity(combined)) moved.store(true, std::memory_order_relaxed);
+            if (node->GetModel() >= models_.size()) continue;
+            const Model& model = models_[node->GetModel()];
+            for (uint32_t section = 0; section < model.SectionCount(); ++section) {
+                NodeProxy& proxy = nodeProxys_[offset[i] + section];
+                proxy = node->GetNodeProxy();
+                memcpy(proxy.combinedPrevTS, combined.data(), 64);
+                proxy.modelId = node->GetModel() * 10 + section;
+                proxy.nort = section == 0 ? 0 : 1;
+            }
+        }
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned threads = n < 16384 ? 1u : std::min(8u, hw);
+    if (threads == 1) fill(0, n);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < threads; ++t) pool.emplace_back(fill, n * t / threads, n * (t + 1) / threads);
+        for (auto& th : pool) th.join();
+    }
+    if (moved.load()) MarkDirty();
     return true;
 }
 
