@@ -46,7 +46,7 @@ WORKLOAD_NAMES = {
     "bricks": "C3: 200k instanced bricks, per-frame TLAS refit, 1920x1080, 1 spp, 4 bounces",
     "city": "C4: 10M-triangle instanced city, 3840x2160, progressive (1 of 64 spp per step), 4 bounces, denoiser off",
 }
-TILE_ROWS = 16
+TILE_ROWS = 16  # rows per tile of the multi-GPU partition; main() shrinks it so that every rank gets >= 32 tiles
 METRIC = "path-tracing throughput (rays traced per second, whole frame incl. reproject + denoise) and ms/frame at the named resolution"
 
 
@@ -171,6 +171,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     scene_name, scene_args, W, H, settings = WORKLOADS[args.workload]
+    global TILE_ROWS
+    if "GK_TILE_ROWS" in os.environ:
+        TILE_ROWS = int(os.environ["GK_TILE_ROWS"])
+    else:  # interleave finely enough that the rounding of tiles per rank stays below ~3 % of a rank's work
+        while TILE_ROWS > 2 and H // (TILE_ROWS * world) < 32:
+            TILE_ROWS //= 2
 
     if args.impl == "reference":
         if rank != 0:
@@ -214,7 +220,7 @@ def main():
 
     local_filters = world > 1 and exchange_mode.startswith("peer") and settings.get("ProgressiveRender", 0) == 1 and settings.get("Denoiser", 1) == 0
     if local_filters:
-        exchange_mode = "filters on owned rows; final image rows pushed peer-to-peer over NVLink to every rank between two 4-byte all-reduce barriers"
+        exchange_mode = "filters on owned rows; final image rows pushed peer-to-peer over NVLink to rank 0 (the presenting rank) between two 4-byte all-reduce barriers"
 
     def frame(step_index, exchange=True):
         if dynamic:
@@ -235,7 +241,7 @@ def main():
             if exchange:
                 xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 xa.record(stream)
-                comp.composite_final(r, rank, world, -1)
+                comp.composite_final(r, rank, world, 0)  # the presenting rank
                 xb.record(stream)
                 xchg_events.append((xa, xb))
             eng.advance_frame()
@@ -294,7 +300,8 @@ def main():
     fin_bytes = r.plane_bytes("DENOISED")
     for i in range(2):
         frame(n_warm + args.steps + i)
-        r.readback_async("DENOISED", final_host[i & 1].data_ptr(), fin_bytes)
+        if rank == 0:
+            r.readback_async("DENOISED", final_host[i & 1].data_ptr(), fin_bytes)
     r.readback_wait()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -303,7 +310,8 @@ def main():
     for i in range(args.steps):
         rr, _, _ = frame(n_warm + args.steps + 2 + i)
         rays_e2e += rr
-        r.readback_async("DENOISED", final_host[i & 1].data_ptr(), fin_bytes)
+        if rank == 0:  # one presenting rank reads the finished image back (the reference presents from one device)
+            r.readback_async("DENOISED", final_host[i & 1].data_ptr(), fin_bytes)
     r.readback_wait()
     e3.record(stream)
     barrier()

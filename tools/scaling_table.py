@@ -1,0 +1,35 @@
+"""profiles/r01_bench/n<N>_<workload>.json -> profiles/r01_scaling.md"""
+import glob
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rows = {}
+for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench", "n*_*.json"))):
+    d = json.load(open(f))
+    if d.get("impl") == "reference":
+        continue
+    rows.setdefault(d["config"]["workload"].split(":")[0], {})[d["n_gpus"]] = d
+out = ["# Round 1: throughput and scaling on B200 (bench.py, 20 timed frames after 5 warm-up frames)\n",
+       "`value` = rays traced by all ranks / max-over-ranks device time; `e2e` adds the UBO upload and the read-back of the final image on the presenting rank.",
+       "Speed-ups are against the 1-GPU line of the same workload; the driver computes its own from the per-N values.\n"]
+for wl, by_n in rows.items():
+    base = by_n.get(1)
+    out.append(f"## {base['config']['workload'] if base else wl}\n")
+    out.append("| GPUs | Mrays/s | ms/frame | speed-up | e2e Mrays/s | trace per rank ms (min..max) | exchange ms | filters ms | tail ms | launches/frame |")
+    out.append("|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|")
+    for n in sorted(by_n):
+        d = by_n[n]
+        b = d["breakdown_ms_per_step"]
+        pr = d.get("per_rank") or {}
+        tr = pr.get("trace_ms")
+        trs = f"{min(tr):.2f}..{max(tr):.2f}" if tr else f"{sum(b[k] for k in ('gen', 'ext', 'shade', 'tail', 'acc')):.2f} (sum of kernels)"
+        sp = f"{d['value'] / base['value']:.2f}x" if base else "-"
+        out.append(f"| {n} | {d['value']:.0f} | {d['ms_per_step']:.2f} | {sp} | {d['e2e']['value']:.0f} | {trs} | {b.get('xchg', 0):.2f} | {b['rep'] + b['jbf']:.2f} | {b['tail']:.2f} | "
+                   f"{d['gpu_launches'] / d['steps'] / n:.0f} |")
+    if base and base.get("cpu_baseline"):
+        c = base["cpu_baseline"]
+        out.append(f"\nCPU baseline on the same box: {c['value']:.1f} Mrays/s on {c['cores']} cores ({c['kind']}: {c['sample']}).")
+    out.append("")
+open(os.path.join(ROOT, "profiles", "r01_scaling.md"), "w").write("\n".join(out) + "\n")
+print("\n".join(out))
