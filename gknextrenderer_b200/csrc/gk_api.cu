@@ -138,6 +138,7 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     if (const char* e = getenv("GK_CONCURRENT_SHADOW")) c.concurrentShadow = atoi(e) != 0;
     if (const char* e = getenv("GK_TRACE_BLOCK")) c.laneBlock = (unsigned)std::min(256, std::max(32, atoi(e) / 32 * 32));
     if (const char* e = getenv("GK_SHADE_BLOCKS")) c.shadeMinBlocks = atoi(e);
+    if (const char* e = getenv("GK_TLAS_PLOC")) c.tlasPloc = atoi(e) != 0;
     if (const char* e = getenv("GK_TLAS_SIZE_BITS")) c.tlasSizeBits = std::min(7, std::max(0, atoi(e)));
     if (const char* e = getenv("GK_SAH_COLLAPSE")) c.sahCollapse = atoi(e) != 0;
     if (const char* e = getenv("GK_TAIL_FRACTION")) c.tailFraction = (float)atof(e);
@@ -170,6 +171,8 @@ void gk_destroy(GkContext* ctx)
     c.dModels.release(), c.dGpuVerts.release(), c.dIndices.release(), c.dMaterials.release(), c.dLights.release(), c.dFaceNormals.release();
     c.dNodes.release(), c.dCubes.release(), c.dVoxels.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dBlasSrc.release(), c.dTlasSrc.release(), c.dInst.release();
     c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release(), c.dRootRef.release();
+    for (int k = 0; k < 2; ++k) c.dPlocRef[k].release(), c.dPlocLo[k].release(), c.dPlocHi[k].release();
+    c.dPlocNn.release(), c.dPlocValid.release(), c.dPlocPos.release();
     c.dCapture.release();
     for (cudaEvent_t e : c.evPool) cudaEventDestroy(e);
     if (c.evFork) cudaEventDestroy(c.evFork);

@@ -22,6 +22,7 @@
 // boxes 32 B r/w, binary node 40 B, wide node 128 B / ~3 prims.
 #include "gk_context.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace gk {
 
@@ -248,7 +249,7 @@ __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left
             const float A = boxAreaOrZero(lx, ly, lz, hx, hy, hz);
             const uint32_t P = last[cur] - first[cur] + 1;
             const float asNode = D[8] + A;
-            const float asLeaf = (P <= leafMax) ? A * (float)P * primCost : kFar;
+            const float asLeaf = (leafMax > 0 && P <= leafMax) ? A * (float)P * primCost : kFar;
             float* o = cost + 8 * (size_t)cur;
             float prev = fminf(asLeaf, asNode);
             o[0] = prev;
@@ -262,6 +263,96 @@ __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left
         cur = parentI[cur];
     }
     if (areaSum && myArea > 0.f) atomicAdd(areaSum, myArea);
+}
+
+// ------------------------------------------------------------------ PLOC topology (TLAS)
+// Parallel locally-ordered clustering (Meister & Bittner 2018): the clusters, kept in Morton order,
+// repeatedly merge with their nearest neighbour (smallest surface area of the union) inside a
+// window of +-kPlocRadius positions when the choice is mutual.  Far better trees than the radix tree
+// of the same order for boxes of mixed size and overlap (instances); costs ~log n rounds of small
+// launches, so it is used when a TLAS is built for keeps, not for per-frame rebuilds of huge ones.
+constexpr int kPlocRadius = 16;
+
+struct PlocClusters {
+    uint32_t* ref; // leaf bit | sorted position, or internal node index
+    float4* lo;
+    float4* hi;
+};
+
+__global__ void k_ploc_init(uint32_t n, const float4* __restrict__ llo, const float4* __restrict__ lhi, PlocClusters C)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    C.ref[i] = kLeafBit | i, C.lo[i] = llo[i], C.hi[i] = lhi[i];
+}
+
+__global__ void k_ploc_nearest(uint32_t m, PlocClusters C, uint32_t* __restrict__ nn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int)m) return;
+    const float4 a = C.lo[i], b = C.hi[i];
+    float best = 3.0e38f;
+    int bestJ = i;
+    uint32_t bestH = 0xffffffffu;
+    const int j0 = max(0, i - kPlocRadius), j1 = min((int)m - 1, i + kPlocRadius);
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const float4 c = C.lo[j], d = C.hi[j];
+        // an empty box (hidden instance: lo > hi) leaves the other box unchanged
+        const float area = boxAreaOrZero(fminf(a.x, c.x), fminf(a.y, c.y), fminf(a.z, c.z), fmaxf(b.x, d.x), fmaxf(b.y, d.y), fmaxf(b.z, d.z));
+        // equal areas (bricks on a lattice) are ordered by a hash of the PAIR, which both partners compute alike:
+        // with "first wins" every cluster of a run would point at its left neighbour and one pair per run would merge
+        const uint32_t lo2 = (uint32_t)min(i, j), hi2 = (uint32_t)max(i, j);
+        uint32_t h = lo2 * 0x9E3779B1u ^ hi2 * 0x85EBCA77u;
+        h ^= h >> 15, h *= 0x2C1B3C6Du, h ^= h >> 12;
+        if (area < best || (area == best && h < bestH)) best = area, bestJ = j, bestH = h;
+    }
+    nn[i] = (uint32_t)bestJ;
+}
+
+__global__ void k_ploc_merge(uint32_t m, PlocClusters C, const uint32_t* __restrict__ nn, uint32_t* __restrict__ valid, uint32_t* __restrict__ nodeCounter,
+                             uint32_t* __restrict__ left, uint32_t* __restrict__ right, uint32_t* __restrict__ parentI, uint32_t* __restrict__ parentL)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t j = nn[i];
+    const bool mutual = j != i && nn[j] == i;
+    if (!mutual) {
+        valid[i] = 1;
+        return;
+    }
+    if (i > j) {
+        valid[i] = 0; // absorbed by its partner
+        return;
+    }
+    const uint32_t id = atomicAdd(nodeCounter, 1u);
+    const uint32_t L = C.ref[i], R = C.ref[j];
+    left[id] = L, right[id] = R;
+    if (L & kLeafBit) parentL[L & 0x7fffffffu] = id; else parentI[L] = id;
+    if (R & kLeafBit) parentL[R & 0x7fffffffu] = id; else parentI[R] = id;
+    const float4 a = C.lo[i], b = C.hi[i], c = C.lo[j], d = C.hi[j];
+    C.ref[i] = id;
+    C.lo[i] = make_float4(fminf(a.x, c.x), fminf(a.y, c.y), fminf(a.z, c.z), 0);
+    C.hi[i] = make_float4(fmaxf(b.x, d.x), fmaxf(b.y, d.y), fmaxf(b.z, d.z), 0);
+    valid[i] = 1;
+}
+
+__global__ void k_ploc_compact(uint32_t m, PlocClusters in, PlocClusters out, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ pos, uint32_t* __restrict__ newCount)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (valid[i]) {
+        const uint32_t p = pos[i];
+        out.ref[p] = in.ref[i], out.lo[p] = in.lo[i], out.hi[p] = in.hi[i];
+    }
+    if (i == m - 1) *newCount = pos[i] + valid[i];
+}
+
+__global__ void k_ploc_finish(PlocClusters C, uint32_t* __restrict__ parentI, uint32_t* __restrict__ rootOut)
+{
+    const uint32_t r = C.ref[0];
+    if (!(r & kLeafBit)) parentI[r] = kInvalid;
+    *rootOut = r;
 }
 
 // ------------------------------------------------------------------ per-group roots
@@ -622,7 +713,7 @@ void Lbvh::release()
 static inline unsigned gridFor(size_t n, unsigned block = 256) { return (unsigned)((n + block - 1) / block); }
 
 // Steps 1-5 over T.plo/T.phi/T.group (group may be null => one group).
-static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint32_t groups, int keyBits, int sizeBits = 0)
+static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint32_t groups, int keyBits, int sizeBits = 0, bool radixTopology = true)
 {
     const uint32_t n = T.n;
     cudaStream_t st = c.stream;
@@ -651,7 +742,7 @@ static GkStatus buildRadixTree(Context& c, Lbvh& T, const uint32_t* group, uint3
     GK_CUDA(c.dSortTemp.reserve(tempBytes));
     tempBytes = c.dSortTemp.bytes();
     GK_CUDA(cub::DeviceRadixSort::SortPairs(c.dSortTemp.p, tempBytes, T.keysAlt.p, T.keys.p, T.orderAlt.p, T.order.p, (int)n, 0, keyBits, st));
-    if (n > 1) k_radix_tree<<<gridFor(n - 1), 256, 0, st>>>(T.keys.p, (int)n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, T.first.p, T.last.p);
+    if (n > 1 && radixTopology) k_radix_tree<<<gridFor(n - 1), 256, 0, st>>>(T.keys.p, (int)n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, T.first.p, T.last.p);
     GK_CUDA(cudaGetLastError());
     return GK_OK;
 }
@@ -683,9 +774,60 @@ static Bvh2View viewOf(const Lbvh& T)
     return B;
 }
 
+// Binary topology of T (left/right/parents) by PLOC over the Morton-sorted leaf boxes; the root reference
+// is left in c.dCounters[7].  keys/order must be in place (buildRadixTree without the radix tree).
+static GkStatus plocTopology(Context& c, Lbvh& T)
+{
+    const uint32_t n = T.n;
+    cudaStream_t st = c.stream;
+    for (int k = 0; k < 2; ++k) {
+        GK_CUDA(c.dPlocRef[k].reserve(n));
+        GK_CUDA(c.dPlocLo[k].reserve(n));
+        GK_CUDA(c.dPlocHi[k].reserve(n));
+    }
+    GK_CUDA(c.dPlocNn.reserve(n));
+    GK_CUDA(c.dPlocValid.reserve(n));
+    GK_CUDA(c.dPlocPos.reserve(n));
+    GK_CUDA(c.dCounters.reserve(8));
+    uint32_t* nodeCounter = c.dCounters.p + 5;
+    uint32_t* newCount = c.dCounters.p + 6;
+    uint32_t* rootOut = c.dCounters.p + 7;
+    GK_CUDA(cudaMemsetAsync(nodeCounter, 0, 3 * sizeof(uint32_t), st));
+    k_leaf_boxes<<<gridFor(n), 256, 0, st>>>(T.plo.p, T.phi.p, T.order.p, n, T.llo.p, T.lhi.p);
+    PlocClusters A{c.dPlocRef[0].p, c.dPlocLo[0].p, c.dPlocHi[0].p}, B{c.dPlocRef[1].p, c.dPlocLo[1].p, c.dPlocHi[1].p};
+    k_ploc_init<<<gridFor(n), 256, 0, st>>>(n, T.llo.p, T.lhi.p, A);
+    size_t tempBytes = 0;
+    GK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, c.dPlocValid.p, c.dPlocPos.p, (int)n, st));
+    GK_CUDA(c.dSortTemp.reserve(tempBytes));
+    uint32_t m = n;
+    for (int round = 0; m > 1; ++round) {
+        if (round > 4096) {
+            setLastError("PLOC did not converge");
+            return GK_ERR_CUDA;
+        }
+        k_ploc_nearest<<<gridFor(m), 256, 0, st>>>(m, A, c.dPlocNn.p);
+        k_ploc_merge<<<gridFor(m), 256, 0, st>>>(m, A, c.dPlocNn.p, c.dPlocValid.p, nodeCounter, T.left.p, T.right.p, T.parentI.p, T.parentL.p);
+        size_t tb = c.dSortTemp.bytes();
+        GK_CUDA(cub::DeviceScan::ExclusiveSum(c.dSortTemp.p, tb, c.dPlocValid.p, c.dPlocPos.p, (int)m, st));
+        k_ploc_compact<<<gridFor(m), 256, 0, st>>>(m, A, B, c.dPlocValid.p, c.dPlocPos.p, newCount);
+        uint32_t next = 0;
+        GK_CUDA(cudaMemcpyAsync(&next, newCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        if (next >= m || next == 0) { // the globally closest pair is always mutual, so every round merges at least one pair
+            setLastError("PLOC made no progress");
+            return GK_ERR_CUDA;
+        }
+        m = next;
+        std::swap(A, B);
+    }
+    k_ploc_finish<<<1, 1, 0, st>>>(A, T.parentI.p, rootOut);
+    GK_CUDA(cudaGetLastError());
+    return GK_OK;
+}
+
 // Step 6+7.  rootRef (device, one per group) receives the wide root reference of each group.
 static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax, bool tlas, DevBuf<WideNode>& nodes, DevBuf<uint32_t>& nodeSrc, uint32_t& nodeCount,
-                         uint32_t* dRootRef, int groupShift = 42)
+                         uint32_t* dRootRef, int groupShift = 42, const uint32_t* dExplicitRoot = nullptr)
 {
     const uint32_t n = T.n;
     cudaStream_t st = c.stream;
@@ -697,9 +839,11 @@ static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax,
     GK_CUDA(c.dCounters.reserve(8));
     GK_CUDA(c.dGroupRoot.reserve(groups));
     GK_CUDA(cudaMemsetAsync(c.dGroupRoot.p, 0xff, sizeof(uint32_t) * groups, st));
+    // single tree whose root is known (it may live in dCounters, which is cleared next)
+    if (dExplicitRoot) GK_CUDA(cudaMemcpyAsync(c.dGroupRoot.p, dExplicitRoot, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     GK_CUDA(cudaMemsetAsync(c.dCounters.p, 0, sizeof(uint32_t) * 8, st));
     const Bvh2View B = viewOf(T);
-    k_group_roots<<<gridFor(n), 256, 0, st>>>(T.keys.p, n, T.first.p, T.last.p, c.dGroupRoot.p, groupShift);
+    if (!dExplicitRoot) k_group_roots<<<gridFor(n), 256, 0, st>>>(T.keys.p, n, T.first.p, T.last.p, c.dGroupRoot.p, groupShift);
     k_collapse_seed<<<gridFor(groups), 256, 0, st>>>(B, c.dGroupRoot.p, groups, leafMax, tlas ? 1 : 0, dRootRef, c.dTaskA.p, c.dCounters.p);
     uint32_t* in = c.dTaskA.p;
     uint32_t* out = c.dTaskB.p;
@@ -785,6 +929,7 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
     GK_CUDA(c.dCounters.reserve(8));
     float* dArea = reinterpret_cast<float*>(c.dCounters.p + 4);
     float area = 0.f;
+    bool guardRebuild = false;
     if (refit) {
         // Refit = new boxes on the old topology.  It is kept only while the tree stays good: the summed
         // surface area of the internal nodes may grow to kRefitGrowthLimit x its value at the last build
@@ -799,18 +944,28 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
             if (c.tlasNodeCount) k_quantise<<<gridFor(c.tlasNodeCount, 128), 128, 0, st>>>(viewOf(T), c.dTlasNodes.p, c.dTlasSrc.p, c.tlasNodeCount);
         } else {
             refit = false;
+            guardRebuild = true;
             c.refitRejected++;
         }
     }
     if (!refit) {
-        s = buildRadixTree(c, T, nullptr, 1, 42 + c.tlasSizeBits, c.tlasSizeBits);
+        // PLOC when the tree is built to last (first build, instance count changed, small scenes); a rebuild forced by the
+        // refit guard on a huge TLAS happens every frame (C3) and keeps the cheaper radix tree
+        const bool ploc = c.tlasPloc && count > 2 && count <= (guardRebuild ? c.tlasPlocMaxRebuild : c.tlasPlocMax);
+        s = buildRadixTree(c, T, nullptr, 1, 42 + c.tlasSizeBits, c.tlasSizeBits, !ploc);
         if (s != GK_OK) return s;
+        if (ploc) {
+            GK_CUDA(cudaMemsetAsync(T.first.p, 0, sizeof(uint32_t) * count, st));
+            GK_CUDA(cudaMemsetAsync(T.last.p, 0, sizeof(uint32_t) * count, st));
+            s = plocTopology(c, T);
+            if (s != GK_OK) return s;
+        }
         GK_CUDA(cudaMemsetAsync(dArea, 0, sizeof(float), st));
         s = propagateBounds(c, T, c.sahCollapse, 0, kCostInstance, dArea);
         if (s != GK_OK) return s;
         GK_CUDA(cudaMemcpyAsync(&c.tlasAreaAtBuild, dArea, sizeof(float), cudaMemcpyDeviceToHost, st));
         GK_CUDA(c.dRootRef.reserve(1));
-        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.dTlasSrc, c.tlasNodeCount, c.dRootRef.p, 42 + c.tlasSizeBits);
+        s = collapse(c, T, 1, 1, true, c.dTlasNodes, c.dTlasSrc, c.tlasNodeCount, c.dRootRef.p, 42 + c.tlasSizeBits, ploc ? c.dCounters.p + 7 : nullptr);
         if (s != GK_OK) return s;
         GK_CUDA(cudaMemcpyAsync(&c.tlasRoot, c.dRootRef.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaStreamSynchronize(st));

@@ -184,6 +184,11 @@ struct Context {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     unsigned laneBlock = 256;       // threads (= rays) per block of the one-ray-per-lane trace kernel
     int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
+    bool tlasPloc = true;           // PLOC topology for the TLAS (false: Karras radix tree)
+    uint32_t tlasPlocMax = 65536;        // ... up to this many instances (no gain measured on 200 k lattice bricks, 37 ms build)
+    uint32_t tlasPlocMaxRebuild = 32768; // guard-forced (per-frame) rebuilds above this many instances keep the radix tree
+    DevBuf<uint32_t> dPlocRef[2], dPlocNn, dPlocValid, dPlocPos;
+    DevBuf<float4> dPlocLo[2], dPlocHi[2];
     int tlasSizeBits = 2;           // extended Morton code of the TLAS: box-size bits woven into the key (0 = plain Morton)
     bool sahCollapse = true;        // cost-driven wide collapse (false: greedy by surface area)
     DevBuf<float4> dCapture;

@@ -952,7 +952,10 @@ GkStatus traceFrame(Context& c)
         const int nxt = cur ^ 1;
         GK_CUDA(cudaMemsetAsync(c.extendQ[nxt].count, 0, sizeof(uint32_t), st));
         GK_CUDA(cudaMemsetAsync(c.shadowQ[nxt].count, 0, sizeof(uint32_t), st));
-        if (c.shadeMinBlocks >= 3)
+        if (c.shadeMinBlocks >= 4)
+            k_shade<4><<<gridFor((size_t)countE + countS), 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.extendQ[nxt],
+                                                                     c.shadowQ[nxt]);
+        else if (c.shadeMinBlocks >= 3)
             k_shade<3><<<gridFor((size_t)countE + countS), 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.extendQ[nxt],
                                                                      c.shadowQ[nxt]);
         else
