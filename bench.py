@@ -273,7 +273,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None  # started before the barrier: NVML start-up must not delay rank 0 inside the timed region
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = dict(rays=0, launches=0, ext=0.0, shd=0.0, shade=0.0, gen=0.0, acc=0.0, rep=0.0, jbf=0.0, bvh=0.0, eray=0, sray=0, pray=0, waves=0, tail=0.0, tail_eray=0, tail_paths=0, ext_launches=0, trace=0.0)
+    agg = dict(rays=0, launches=0, ext=0.0, shd=0.0, shade=0.0, gen=0.0, acc=0.0, rep=0.0, jbf=0.0, bvh=0.0, eray=0, sray=0, pray=0, waves=0, tail=0.0, tail_eray=0, tail_paths=0, ext_launches=0, trace=0.0, trace_kernels=0.0, tail_sray=0)
     xchg_events.clear()
     e0.record(stream)
     t_wall = time.perf_counter()
@@ -283,7 +283,7 @@ def main():
         agg["ext"] += st.msExtend; agg["shd"] += st.msShadow; agg["shade"] += st.msShade; agg["gen"] += st.msGenerate; agg["acc"] += st.msAccumulate
         agg["rep"] += st.msReproject; agg["jbf"] += st.msDenoise; agg["bvh"] += st.msBvh if dynamic else 0.0
         agg["eray"] += st.extensionRays; agg["sray"] += st.shadowRays; agg["pray"] += st.primaryRays; agg["waves"] += st.waves
-        agg["trace"] += st.msTotal
+        agg["trace"] += st.msTotal; agg["trace_kernels"] += st.msTrace; agg["tail_sray"] += st.tailShadowRays
         agg["tail"] += st.msTail; agg["tail_eray"] += st.tailExtensionRays; agg["tail_paths"] += st.tailPaths; agg["ext_launches"] += st.waves - (1 if st.tailPaths else 0)
     e1.record(stream)
     barrier()
@@ -352,8 +352,10 @@ def main():
     nodes_per_ray = st1.nodeVisits / max(traced, 1)
     tris_per_ray = st1.triTests / max(traced, 1)
     bytes_per_ray = 48.0 + 128.0 * nodes_per_ray + 48.0 * tris_per_ray  # ray 32 + hit 16, 128-B node lines, 48-B triangle records
-    ext_rays = agg["eray"] + agg["pray"] - agg["tail_eray"]  # closest-hit rays traced by k_trace launches (the tail launch traces its own)
-    ext_ms = agg["ext"]
+    # rays traced by the k_trace launches of the waves (closest hit + any hit; the tail launch traces its own) and the
+    # time those launches take: extend and shadow kernel of a wave run concurrently, so they are timed as one span
+    ext_rays = agg["eray"] + agg["pray"] - agg["tail_eray"] + agg["sray"] - agg["tail_sray"]
+    ext_ms = agg["trace_kernels"]
     l2_peak = measure_l2_bandwidth(torch)
     achieved = ext_rays * bytes_per_ray / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
     peaks = {}
@@ -369,15 +371,15 @@ def main():
         pass
     px = W * H
     filt_ms = (agg["rep"] + agg["jbf"]) / args.steps
-    roofline = {"kernel": "k_trace<closest hit> (extend: traversal of the 8-wide quantised two-level BVH)", "bound": "l2", "achieved": round(achieved, 1), "peak": round(l2_peak, 1), "unit": "GB/s",
+    roofline = {"kernel": "k_trace (extend + shadow launches of the waves: traversal of the 8-wide quantised two-level BVH; the two run concurrently and are timed as one span)", "bound": "l2", "achieved": round(achieved, 1), "peak": round(l2_peak, 1), "unit": "GB/s",
                 "frac": round(achieved / l2_peak, 4) if l2_peak else None,
                 "traffic": traffic.get("dram_bytes_per_launch_avg") if args.workload == "room" and world == 1 else None,
                 "traffic_source": traffic.get("source") if args.workload == "room" and world == 1 else None,
-                "algorithmic_bytes_per_launch": round(bytes_per_ray * ext_rays / max(agg["ext_launches"], 1), 0),
+                "algorithmic_bytes_per_wave": round(bytes_per_ray * ext_rays / max(agg["ext_launches"], 1), 0),
                 "note": "achieved = L2-level algorithmic bytes (48 B ray/hit + 128 B per node visit + 48 B per triangle test, counted by an instrumented frame) / kernel time; "
-                        "traffic = DRAM bytes per launch from ncu: only the compulsory 52 B/ray reach HBM, the node/triangle bytes are served by L1/L2 (SURVEY 8d: this kernel is L2/issue bound)",
+                        "traffic = DRAM bytes per wave (its extend + shadow launch) from ncu: only the compulsory ~51 B/ray reach HBM, the node/triangle bytes are served by L1/L2 (SURVEY 8d: this kernel is L2/issue bound)",
                 "model": {"bytes_per_ray": round(bytes_per_ray, 1), "node_visits_per_ray": round(nodes_per_ray, 2), "tri_tests_per_ray": round(tris_per_ray, 2),
-                          "rays_per_launch_avg": round(ext_rays / max(agg["ext_launches"], 1), 0), "launches_per_step": round(agg["ext_launches"] / args.steps, 1), "ms_per_step": round(ext_ms / args.steps, 4),
+                          "rays_per_wave_avg": round(ext_rays / max(agg["ext_launches"], 1), 0), "waves_per_step": round(agg["ext_launches"] / args.steps, 1), "ms_per_step": round(ext_ms / args.steps, 4),
                           "Grays_per_s_in_kernel": round(ext_rays / (ext_ms * 1e-3) / 1e9, 4) if ext_ms > 0 else None},
                 "peak_source": "measured in this run: torch.sum over an L2-resident 48 MB buffer"}
     roofline_filters = {"kernel": "k_reproject + k_denoise_jbf", "bound": "hbm", "achieved": round((96 + 48) * px / (filt_ms * 1e-3) / 1e9, 1) if filt_ms > 0 else None,
@@ -403,7 +405,7 @@ def main():
         "rays_per_step": round(total_rays / args.steps, 0), "gpu_launches": total_launches,
         "e2e": {"value": round(total_rays_e2e / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "api": "CudaPathTracingRenderer::BeforeNextFrame + Render (host mirror of LogicRendererBase) + gk_readback_async(rtDenoised) to pinned memory, double-buffered"},
-        "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "shade", "tail", "acc", "xchg", "rep", "jbf", "bvh")},
+        "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("gen", "ext", "shd", "trace_kernels", "shade", "tail", "acc", "xchg", "rep", "jbf", "bvh")},
         "per_rank": per_rank,
         "tail_paths_per_step": round(agg["tail_paths"] / args.steps, 0),
         "host_gap_ms_per_step": round((wall_ms - dev_ms) / args.steps, 4),

@@ -116,7 +116,7 @@ class GkFrameStats(C.Structure):
                 ("msShade", C.c_float), ("msShadow", C.c_float), ("msAccumulate", C.c_float), ("msReproject", C.c_float),
                 ("msDenoise", C.c_float), ("nodeVisits", C.c_uint64), ("triTests", C.c_uint64),
                 ("tlasVisits", C.c_uint64), ("instanceEntries", C.c_uint64), ("msTail", C.c_float), ("tailPaths", C.c_uint32),
-                ("tailExtensionRays", C.c_uint64), ("tailShadowRays", C.c_uint64), ("maxStack", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("tailExtensionRays", C.c_uint64), ("tailShadowRays", C.c_uint64), ("maxStack", C.c_uint32), ("msTrace", C.c_float)]
 
 
 class GkBvhInfo(C.Structure):

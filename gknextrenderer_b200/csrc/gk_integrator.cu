@@ -866,7 +866,7 @@ GkStatus traceFrame(Context& c)
     GkFrameStats& fs = c.stats;
     fs.primaryRays = fs.extensionRays = fs.shadowRays = 0;
     fs.waves = fs.launches = 0;
-    fs.msGenerate = fs.msExtend = fs.msShade = fs.msShadow = fs.msAccumulate = fs.msTail = 0;
+    fs.msGenerate = fs.msExtend = fs.msShade = fs.msShadow = fs.msAccumulate = fs.msTail = fs.msTrace = 0;
     size_t ev = 0;
     struct Span { size_t a, b; int kind; };
     std::vector<Span> spans;
@@ -963,7 +963,7 @@ GkStatus traceFrame(Context& c)
                                                                      c.shadowQ[nxt]);
         fs.launches++;
         const size_t f = mark();
-        spans.push_back({a, b, 1}), spans.push_back({d, f, 3});
+        spans.push_back({a, b, 1}), spans.push_back({d, f, 3}), spans.push_back({a, d, 6});
         if (fork) spans.push_back({s0, s1, 2}); // overlaps the extend span
         else spans.push_back({b, d, 2});
         GK_CUDA(cudaMemcpyAsync(c.hCounts, c.extendQ[nxt].count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -990,6 +990,7 @@ GkStatus traceFrame(Context& c)
         else if (s.kind == 2) fs.msShadow += ms;
         else if (s.kind == 3) fs.msShade += ms;
         else if (s.kind == 5) fs.msTail += ms;
+        else if (s.kind == 6) fs.msTrace += ms;
         else fs.msAccumulate += ms;
     }
     cudaEventElapsedTime(&fs.msTotal, c.evPool[evStart], c.evPool[hEnd]);

@@ -98,7 +98,7 @@ typedef struct GkFrameStats {
     uint32_t tailPaths; /* paths alive when that launch started */
     uint64_t tailExtensionRays, tailShadowRays; /* part of extensionRays / shadowRays traced by that launch */
     uint32_t maxStack;  /* traversal statistics: deepest stack seen; GK_TRAVERSAL_STACK + 1 means an entry was dropped */
-    uint32_t reserved0;
+    float msTrace;      /* extend + shadow kernels of all waves as one span per wave (the two run concurrently) */
 } GkFrameStats;
 
 typedef struct GkBvhInfo {
