@@ -139,6 +139,7 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     if (const char* e = getenv("GK_TRACE_BLOCK")) c.laneBlock = (unsigned)std::min(256, std::max(32, atoi(e) / 32 * 32));
     if (const char* e = getenv("GK_SHADE_BLOCKS")) c.shadeMinBlocks = atoi(e);
     if (const char* e = getenv("GK_TLAS_PLOC")) c.tlasPloc = atoi(e) != 0;
+    if (const char* e = getenv("GK_TLAS_PLOC_RADIUS")) c.tlasPlocRadius = std::min(256, std::max(1, atoi(e)));
     if (const char* e = getenv("GK_TLAS_SIZE_BITS")) c.tlasSizeBits = std::min(7, std::max(0, atoi(e)));
     if (const char* e = getenv("GK_SAH_COLLAPSE")) c.sahCollapse = atoi(e) != 0;
     if (const char* e = getenv("GK_TAIL_FRACTION")) c.tailFraction = (float)atof(e);

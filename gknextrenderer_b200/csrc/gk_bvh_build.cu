@@ -268,10 +268,9 @@ __global__ void k_propagate_bounds(uint32_t n, const uint32_t* __restrict__ left
 // ------------------------------------------------------------------ PLOC topology (TLAS)
 // Parallel locally-ordered clustering (Meister & Bittner 2018): the clusters, kept in Morton order,
 // repeatedly merge with their nearest neighbour (smallest surface area of the union) inside a
-// window of +-kPlocRadius positions when the choice is mutual.  Far better trees than the radix tree
+// window of +-radius positions (Context::tlasPlocRadius) when the choice is mutual.  Far better trees than the radix tree
 // of the same order for boxes of mixed size and overlap (instances); costs ~log n rounds of small
 // launches, so it is used when a TLAS is built for keeps, not for per-frame rebuilds of huge ones.
-constexpr int kPlocRadius = 16;
 
 struct PlocClusters {
     uint32_t* ref; // leaf bit | sorted position, or internal node index
@@ -286,7 +285,7 @@ __global__ void k_ploc_init(uint32_t n, const float4* __restrict__ llo, const fl
     C.ref[i] = kLeafBit | i, C.lo[i] = llo[i], C.hi[i] = lhi[i];
 }
 
-__global__ void k_ploc_nearest(uint32_t m, PlocClusters C, uint32_t* __restrict__ nn)
+__global__ void k_ploc_nearest(uint32_t m, PlocClusters C, uint32_t* __restrict__ nn, int radius)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int)m) return;
@@ -294,7 +293,7 @@ __global__ void k_ploc_nearest(uint32_t m, PlocClusters C, uint32_t* __restrict_
     float best = 3.0e38f;
     int bestJ = i;
     uint32_t bestH = 0xffffffffu;
-    const int j0 = max(0, i - kPlocRadius), j1 = min((int)m - 1, i + kPlocRadius);
+    const int j0 = max(0, i - radius), j1 = min((int)m - 1, i + radius);
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
         const float4 c = C.lo[j], d = C.hi[j];
@@ -805,7 +804,7 @@ static GkStatus plocTopology(Context& c, Lbvh& T)
             setLastError("PLOC did not converge");
             return GK_ERR_CUDA;
         }
-        k_ploc_nearest<<<gridFor(m), 256, 0, st>>>(m, A, c.dPlocNn.p);
+        k_ploc_nearest<<<gridFor(m), 256, 0, st>>>(m, A, c.dPlocNn.p, c.tlasPlocRadius);
         k_ploc_merge<<<gridFor(m), 256, 0, st>>>(m, A, c.dPlocNn.p, c.dPlocValid.p, nodeCounter, T.left.p, T.right.p, T.parentI.p, T.parentL.p);
         size_t tb = c.dSortTemp.bytes();
         GK_CUDA(cub::DeviceScan::ExclusiveSum(c.dSortTemp.p, tb, c.dPlocValid.p, c.dPlocPos.p, (int)m, st));

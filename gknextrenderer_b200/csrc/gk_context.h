@@ -185,6 +185,7 @@ struct Context {
     unsigned laneBlock = 256;       // threads (= rays) per block of the one-ray-per-lane trace kernel
     int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
     bool tlasPloc = true;           // PLOC topology for the TLAS (false: Karras radix tree)
+    int tlasPlocRadius = 64;             // search window of the nearest-neighbour pass
     uint32_t tlasPlocMax = 65536;        // ... up to this many instances (no gain measured on 200 k lattice bricks, 37 ms build)
     uint32_t tlasPlocMaxRebuild = 32768; // guard-forced (per-frame) rebuilds above this many instances keep the radix tree
     DevBuf<uint32_t> dPlocRef[2], dPlocNn, dPlocValid, dPlocPos;
