@@ -131,11 +131,12 @@ class Engine:
 class Renderer:
     """One GkContext: the CUDA path tracer behind the C ABI."""
 
-    def __init__(self, width, height, device=-1, tile_index=0, tile_count=1, tile_rows=16):
+    def __init__(self, width, height, device=-1, tile_index=0, tile_count=1, tile_rows=16, trace_all_rows=False):
         self.lib = cuda_lib()
         cfg = GkConfig()
         cfg.device, cfg.width, cfg.height = device, width, height
         cfg.tileIndex, cfg.tileCount, cfg.tileRows = tile_index, tile_count, tile_rows
+        cfg.flags = 1 if trace_all_rows else 0  # GK_CFG_TRACE_ALL_ROWS
         h = C.c_void_p()
         self._check(self.lib.gk_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -254,6 +255,20 @@ class Renderer:
 
     def exchange_push_final(self, dst_rank: int = -1):
         self._check(self.lib.gk_exchange_push_final(self.h, dst_rank))
+
+    def frame_shard_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.gk_frame_shard_handle(self.h, buf, 64))
+        return buf.raw
+
+    def frame_shard_open(self, handles_all: bytes, world: int):
+        self._check(self.lib.gk_frame_shard_open(self.h, handles_all, world))
+
+    def frame_shard_push(self):
+        self._check(self.lib.gk_frame_shard_push(self.h))
+
+    def frame_shard_accumulate(self):
+        self._check(self.lib.gk_frame_shard_accumulate(self.h))
 
     def exchange_push(self):
         self._check(self.lib.gk_exchange_push(self.h))

@@ -157,6 +157,10 @@ CUDA_API = {
     "gk_exchange_ipc_handles": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "gk_exchange_open_peers": (C.c_int, [_P, C.c_void_p, C.c_uint32]),
     "gk_exchange_push": (C.c_int, [_P]),
+    "gk_frame_shard_handle": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
+    "gk_frame_shard_open": (C.c_int, [_P, C.c_void_p, C.c_uint32]),
+    "gk_frame_shard_push": (C.c_int, [_P]),
+    "gk_frame_shard_accumulate": (C.c_int, [_P]),
     "gk_filter_frame_owned": (C.c_int, [_P]),
     "gk_exchange_push_final": (C.c_int, [_P, C.c_int]),
     "gk_host_alloc": (C.c_void_p, [C.c_size_t]),

@@ -183,3 +183,47 @@ def composite_final(renderer, rank: int, world: int, dst_rank: int = -1, group=N
     with torch.cuda.stream(stream):
         dist.all_reduce(token, group=group)
     return renderer.plane_bytes("DENOISED") // world
+
+
+_shard = set()
+
+
+def enable_frame_sharding(renderer, rank: int, world: int, group=None) -> bool:
+    """Frame-sharded progressive rendering: map the gather buffers of all ranks (CUDA IPC).  The renderer
+    must have been created with trace_all_rows=True; enable_peer_exchange() must have succeeded."""
+    import torch
+    import torch.distributed as dist
+    hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if world == 1 or hkey not in _p2p:
+        return False
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    mine = torch.frombuffer(bytearray(renderer.frame_shard_handle()), dtype=torch.uint8).to(dev)
+    every = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    renderer.frame_shard_open(bytes(every.cpu().numpy().tobytes()), world)
+    dist.barrier(group=group)
+    _shard.add(hkey)
+    return True
+
+
+def composite_frame_shard(renderer, rank: int, world: int, dst_rank: int = 0, group=None):
+    """Super-step of frame-sharded progressive rendering, after every rank traced ITS frame (gk_trace_frame with
+    TotalFrames = f0 + rank): rows go to their owners, the owners accumulate the `world` frames in order and
+    compose, the finished rows go to the presenting rank.  Three stream barriers per super-step."""
+    import torch
+    import torch.distributed as dist
+    hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if hkey not in _shard:
+        raise RuntimeError("composite_frame_shard needs enable_frame_sharding()")
+    token, stream = _p2p[hkey]
+    renderer.readback_wait()
+    with torch.cuda.stream(stream):
+        dist.all_reduce(token, group=group)  # every rank has consumed the gather buffers / rtDenoised of the last super-step
+    renderer.frame_shard_push()
+    with torch.cuda.stream(stream):
+        dist.all_reduce(token, group=group)  # all rows have landed
+    renderer.frame_shard_accumulate()
+    renderer.exchange_push_final(dst_rank)
+    with torch.cuda.stream(stream):
+        dist.all_reduce(token, group=group)  # the presenting rank holds the whole image
+    return 3 * 8 * renderer.width * renderer.height * (world - 1) // world

@@ -132,12 +132,15 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     c.tileIndex = cfg->tileIndex;
     c.tileRows = cfg->tileRows ? cfg->tileRows : 16;
     c.flags = cfg->flags;
+    c.traceTileIndex = (c.flags & GK_CFG_TRACE_ALL_ROWS) ? 0u : c.tileIndex;
+    c.traceTileCount = (c.flags & GK_CFG_TRACE_ALL_ROWS) ? 1u : c.tileCount;
     // measured on the 1080p room (sweep 16 K .. 4 M paths): the one-launch tail wins below ~2.5-3.5 K paths per SM (1 and 2 GPUs)
     c.tailThreshold = 3584u * (uint32_t)prop.multiProcessorCount;
     if (const char* e = getenv("GK_BLAS_LEAF")) c.blasLeafMax = (uint32_t)std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("GK_CONCURRENT_SHADOW")) c.concurrentShadow = atoi(e) != 0;
     if (const char* e = getenv("GK_TRACE_BLOCK")) c.laneBlock = (unsigned)std::min(256, std::max(32, atoi(e) / 32 * 32));
     if (const char* e = getenv("GK_SHADE_BLOCKS")) c.shadeMinBlocks = atoi(e);
+    if (const char* e = getenv("GK_COST_TRI")) c.costTri = (float)atof(e);
     if (const char* e = getenv("GK_TLAS_PLOC")) c.tlasPloc = atoi(e) != 0;
     if (const char* e = getenv("GK_TLAS_PLOC_RADIUS")) c.tlasPlocRadius = std::min(256, std::max(1, atoi(e)));
     if (const char* e = getenv("GK_TLAS_SIZE_BITS")) c.tlasSizeBits = std::min(7, std::max(0, atoi(e)));
@@ -462,6 +465,30 @@ GkStatus gk_exchange_push_final(GkContext* ctx, int dst_rank)
 {
     GK_CHECK_CTX(ctx);
     return exchangePushFinal(c, dst_rank);
+}
+
+GkStatus gk_frame_shard_handle(GkContext* ctx, void* out, size_t bytes)
+{
+    GK_CHECK_CTX(ctx);
+    return frameShardHandle(c, out, bytes);
+}
+
+GkStatus gk_frame_shard_open(GkContext* ctx, const void* handles_all, uint32_t world)
+{
+    GK_CHECK_CTX(ctx);
+    return frameShardOpen(c, handles_all, world);
+}
+
+GkStatus gk_frame_shard_push(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    return frameShardPush(c);
+}
+
+GkStatus gk_frame_shard_accumulate(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    return frameShardAccumulate(c);
 }
 
 GkStatus gk_exchange_push(GkContext* ctx)

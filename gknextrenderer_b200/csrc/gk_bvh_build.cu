@@ -180,7 +180,6 @@ __global__ void k_leaf_boxes(const float4* __restrict__ plo, const float4* __res
 }
 
 // Cost model of the wide collapse (node visit = 1): one triangle test, one instance entry.
-constexpr float kCostTri = 0.3f;
 constexpr float kCostInstance = 1.5f;
 constexpr float kRefitGrowthLimit = 1.25f;
 
@@ -884,7 +883,7 @@ GkStatus buildBlasForest(Context& c)
     if (s != GK_OK) return s;
     GK_CUDA(c.dTris.reserve(T.n));
     k_write_tri_records<<<gridFor(T.n), 256, 0, st>>>(sceneTriPositions().p, T.order.p, c.dModels.p, T.group.p, T.n, c.dTris.p);
-    s = propagateBounds(c, T, c.sahCollapse, c.blasLeafMax, kCostTri);
+    s = propagateBounds(c, T, c.sahCollapse, c.blasLeafMax, c.costTri);
     if (s != GK_OK) return s;
     DevBuf<uint32_t> rootRef;
     GK_CUDA(rootRef.reserve(groups));

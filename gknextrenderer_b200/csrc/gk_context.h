@@ -117,6 +117,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     uint32_t width = 0, height = 0;
     uint32_t tileIndex = 0, tileCount = 1, tileRows = 16;
+    uint32_t traceTileIndex = 0, traceTileCount = 1; // rows the path tracer covers (== tileIndex/tileCount unless GK_CFG_TRACE_ALL_ROWS)
     uint32_t ownedRows = 0, pathCount = 0;
     uint32_t flags = 0;
 
@@ -172,6 +173,11 @@ struct Context {
     std::vector<cudaEvent_t> evPool;
     int captureWave = -1;
     PeerExchange peers;
+    // frame-sharded progressive rendering: sources of the `world` frames of a super-step for the rows this rank owns
+    uint2* shardGather = nullptr; // [source rank][3 planes][owned row][x]
+    size_t shardSlotPixels = 0;   // pixels of one plane of one source
+    void* shardPeer[kMaxPeers] = {};
+    bool shardOpen = false;
     // asynchronous read-back (gk_readback_async): copy stream + the buffer it is still reading
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evCopyReady = nullptr, evCopyDone = nullptr;
@@ -185,6 +191,7 @@ struct Context {
     unsigned laneBlock = 256;       // threads (= rays) per block of the one-ray-per-lane trace kernel
     int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
     bool tlasPloc = true;           // PLOC topology for the TLAS (false: Karras radix tree)
+    float costTri = 0.3f;                // collapse cost model: one triangle test relative to one node visit
     int tlasPlocRadius = 64;             // search window of the nearest-neighbour pass
     uint32_t tlasPlocMax = 65536;        // ... up to this many instances (no gain measured on 200 k lattice bricks, 37 ms build)
     uint32_t tlasPlocMaxRebuild = 32768; // guard-forced (per-frame) rebuilds above this many instances keep the radix tree
@@ -229,6 +236,12 @@ GkStatus exchangeOpenPeers(Context& c, const void* handlesAll, uint32_t world);
 void waitAsyncCopyBeforeWriting(Context& c, const void* const* buffers, int count); // orders the stream after an in-flight read-back of any of them
 GkStatus exchangePush(Context& c);
 GkStatus exchangePushFinal(Context& c, int dstRank);
+GkStatus frameShardHandle(Context& c, void* out, size_t bytes);
+GkStatus frameShardOpen(Context& c, const void* handlesAll, uint32_t world);
+GkStatus frameShardPush(Context& c);
+GkStatus frameShardAccumulate(Context& c);
+void frameShardRelease(Context& c);
+GkStatus composeOwnedRows(Context& c); // gk_filters.cu: k_denoise_jbf on the owned rows + history hand-over
 GkStatus filterFrameOwnedRows(Context& c);
 void exchangeClosePeers(Context& c);
 

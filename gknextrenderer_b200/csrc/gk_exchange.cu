@@ -10,6 +10,7 @@
 // after which each rank filters the whole image locally (halos need no further traffic).
 // Both kernels are pure streaming copies in 4-byte words, coalesced along rows.
 #include "gk_context.h"
+#include <cuda_fp16.h>
 
 namespace gk {
 
@@ -100,7 +101,183 @@ __global__ void __launch_bounds__(256) k_exchange_push(PushArgs A)
     }
 }
 
+// ---- frame-sharded progressive rendering -------------------------------------------------------
+// Rank s has traced the whole frame f0 + s.  k_shard_push sends every row of its three source planes
+// (diffuse, specular, albedo) to the rank that owns the row: slot s of that rank's gather buffer.
+struct ShardPushArgs {
+    const uint2* src[3];
+    uint2* dst[kMaxPeers]; // gather buffer of every rank (own one included)
+    uint64_t slotPixels;   // pixels of one plane of one source slot
+    uint32_t width, height, tileRows, world, rank;
+};
+
+__global__ void __launch_bounds__(256) k_shard_push(ShardPushArgs A)
+{
+    const uint32_t y = blockIdx.y, p = blockIdx.z;
+    const uint32_t tile = y / A.tileRows;
+    const uint32_t owner = tile % A.world;
+    const uint32_t lrow = (tile / A.world) * A.tileRows + y % A.tileRows; // row inside the owner's share
+    const uint2* s = A.src[p] + (uint64_t)y * A.width;
+    uint2* d = A.dst[owner] + ((uint64_t)A.rank * 3 + p) * A.slotPixels + (uint64_t)lrow * A.width;
+    if ((A.width & 1u) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(s);
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.width / 2; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+    } else {
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.width; i += gridDim.x * blockDim.x) d[i] = s[i];
+    }
+}
+
+struct ShardAccArgs {
+    const uint2* gather;
+    const uint2* hist[3];
+    uint2* out[3];
+    uint64_t slotPixels;
+    uint32_t width, height, tileRows, world, rank;
+    float keep; // 1 / TemporalFrames, clamped (ReProject:76-82)
+};
+
+__device__ __forceinline__ float3 unpackHalf3(uint2 v)
+{
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return make_float3(a.x, a.y, b.x);
+}
+__device__ __forceinline__ uint2 packHalf4(float3 c, float a)
+{
+    const __half2 lo = __floats2half2_rn(c.x, c.y), hi = __floats2half2_rn(c.z, a);
+    uint2 v;
+    v.x = *reinterpret_cast<const uint32_t*>(&lo), v.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return v;
+}
+
+// One thread per owned pixel: history <- lerp(history, src_s, keep) for the frames s = 0..world-1 in order,
+// rounded to RGBA16F after every step like `world` consecutive single-GPU frames (lerp(a,b,t) = a*(1-t) + b*t).
+__global__ void __launch_bounds__(256) k_shard_accumulate(ShardAccArgs A)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, lrow = blockIdx.y;
+    const uint32_t y = ((lrow / A.tileRows) * A.world + A.rank) * A.tileRows + lrow % A.tileRows;
+    if (x >= A.width || y >= A.height) return;
+    const uint64_t pi = (uint64_t)y * A.width + x, li = (uint64_t)lrow * A.width + x;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        uint2 packed = A.hist[ch][pi];
+        for (uint32_t s = 0; s < A.world; ++s) {
+            const float3 h = unpackHalf3(packed);
+            const float3 c = unpackHalf3(A.gather[((uint64_t)s * 3 + ch) * A.slotPixels + li]);
+            const float k = A.keep;
+            packed = packHalf4(make_float3(h.x * (1.0f - k) + c.x * k, h.y * (1.0f - k) + c.y * k, h.z * (1.0f - k) + c.z * k), 1.0f);
+        }
+        A.out[ch][pi] = packed;
+    }
+}
+
 } // namespace
+
+static uint32_t shardRowsPadded(const Context& c) { return ((c.height + c.tileRows * c.tileCount - 1) / (c.tileRows * c.tileCount)) * c.tileRows; }
+
+void frameShardRelease(Context& c)
+{
+    if (c.shardOpen)
+        for (uint32_t r = 0; r < c.tileCount && r < (uint32_t)kMaxPeers; ++r)
+            if (r != c.tileIndex && c.shardPeer[r]) cudaIpcCloseMemHandle(c.shardPeer[r]);
+    for (int r = 0; r < kMaxPeers; ++r) c.shardPeer[r] = nullptr;
+    c.shardOpen = false;
+    if (c.shardGather) cudaFree(c.shardGather);
+    c.shardGather = nullptr;
+}
+
+GkStatus frameShardHandle(Context& c, void* out, size_t bytes)
+{
+    if (!out || bytes < sizeof(cudaIpcMemHandle_t)) {
+        setLastError("gk_frame_shard_handle: buffer too small");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    if (!(c.flags & GK_CFG_TRACE_ALL_ROWS) || c.tileCount > (uint32_t)kMaxPeers) {
+        setLastError("gk_frame_shard_handle: the context must be created with GK_CFG_TRACE_ALL_ROWS (and <= 16 ranks)");
+        return GK_ERR_UNSUPPORTED;
+    }
+    if (!c.shardGather) {
+        c.shardSlotPixels = (size_t)shardRowsPadded(c) * c.width;
+        GK_CUDA(cudaMalloc(&c.shardGather, sizeof(uint2) * c.shardSlotPixels * 3 * c.tileCount));
+        GK_CUDA(cudaMemsetAsync(c.shardGather, 0, sizeof(uint2) * c.shardSlotPixels * 3 * c.tileCount, c.stream));
+        GK_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    GK_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(out), c.shardGather));
+    return GK_OK;
+}
+
+GkStatus frameShardOpen(Context& c, const void* handlesAll, uint32_t world)
+{
+    if (!handlesAll || world != c.tileCount || !c.shardGather) {
+        setLastError("gk_frame_shard_open: call gk_frame_shard_handle first; world must equal GkConfig.tileCount");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handlesAll);
+    for (uint32_t r = 0; r < world; ++r) {
+        if (r == c.tileIndex) {
+            c.shardPeer[r] = c.shardGather;
+            continue;
+        }
+        const cudaError_t e = cudaIpcOpenMemHandle(&c.shardPeer[r], h[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            setLastError(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+            return GK_ERR_CUDA;
+        }
+    }
+    c.shardOpen = true;
+    return GK_OK;
+}
+
+GkStatus frameShardPush(Context& c)
+{
+    if (!c.shardOpen) {
+        setLastError("gk_frame_shard_push: gather buffers not opened");
+        return GK_ERR_NOT_READY;
+    }
+    ShardPushArgs A;
+    A.src[0] = (const uint2*)c.planes.p[GK_PLANE_OUTPUT_DIFFUSE], A.src[1] = (const uint2*)c.planes.p[GK_PLANE_OUTPUT_SPECULAR], A.src[2] = (const uint2*)c.planes.p[GK_PLANE_ALBEDO];
+    for (int r = 0; r < kMaxPeers; ++r) A.dst[r] = (uint2*)c.shardPeer[r];
+    A.slotPixels = c.shardSlotPixels;
+    A.width = c.width, A.height = c.height, A.tileRows = c.tileRows, A.world = c.tileCount, A.rank = c.tileIndex;
+    const dim3 grid((c.width / 2 + 255) / 256, c.height, 3);
+    k_shard_push<<<grid, 256, 0, c.stream>>>(A);
+    GK_CUDA(cudaGetLastError());
+    c.stats.launches += 1;
+    return GK_OK;
+}
+
+GkStatus frameShardAccumulate(Context& c)
+{
+    if (!c.shardOpen || !c.haveUbo) {
+        setLastError("gk_frame_shard_accumulate: gather buffers and UBO must be set");
+        return GK_ERR_NOT_READY;
+    }
+    if (!(c.ubo.ProgressiveRender != 0 && c.ubo.BFSize == 0)) {
+        setLastError("gk_frame_shard_accumulate: needs ProgressiveRender != 0 and BFSize == 0");
+        return GK_ERR_UNSUPPORTED;
+    }
+    applyPendingHistorySwap(c); // the accumulated planes of the last super-step become the history
+    GK_CUDA(cudaMemcpyAsync(c.dUbo, &c.ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, c.stream));
+    void** P = c.planes.p;
+    ShardAccArgs A;
+    A.gather = c.shardGather;
+    A.hist[0] = (const uint2*)P[GK_PLANE_HISTORY_DIFFUSE], A.hist[1] = (const uint2*)P[GK_PLANE_HISTORY_SPECULAR], A.hist[2] = (const uint2*)P[GK_PLANE_HISTORY_ALBEDO];
+    A.out[0] = (uint2*)P[GK_PLANE_ACCUM_DIFFUSE], A.out[1] = (uint2*)P[GK_PLANE_ACCUM_SPECULAR], A.out[2] = (uint2*)P[GK_PLANE_ACCUM_ALBEDO];
+    A.slotPixels = c.shardSlotPixels;
+    A.width = c.width, A.height = c.height, A.tileRows = c.tileRows, A.world = c.tileCount, A.rank = c.tileIndex;
+    const float t = 1.0f / float(c.ubo.TemporalFrames);
+    A.keep = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+    {
+        const void* bufs[] = {P[GK_PLANE_ACCUM_DIFFUSE], P[GK_PLANE_ACCUM_SPECULAR], P[GK_PLANE_ACCUM_ALBEDO]};
+        waitAsyncCopyBeforeWriting(c, bufs, 3);
+    }
+    const dim3 grid((c.width + 255) / 256, shardRowsPadded(c), 1);
+    k_shard_accumulate<<<grid, 256, 0, c.stream>>>(A);
+    GK_CUDA(cudaGetLastError());
+    c.stats.launches += 1;
+    return composeOwnedRows(c);
+}
 
 GkStatus exchangeIpcHandles(Context& c, void* out, size_t bytes)
 {

@@ -420,6 +420,30 @@ static GkStatus runFilters(Context& c, bool ownedRowsOnly)
     return GK_OK;
 }
 
+// Compose + tonemap (k_denoise_jbf) of the rows this context owns from the accumulated planes, then the
+// history hand-over.  Used by the frame-sharded accumulation, which writes the accumulated planes itself.
+GkStatus composeOwnedRows(Context& c)
+{
+    cudaStream_t st = c.stream;
+    void** P = c.planes.p;
+    DenoiseArgs D;
+    D.diffuse = (const uint2*)P[GK_PLANE_ACCUM_DIFFUSE], D.spec = (const uint2*)P[GK_PLANE_ACCUM_SPECULAR], D.albedo = (const uint2*)P[GK_PLANE_ACCUM_ALBEDO];
+    D.id0 = (const uint32_t*)P[GK_PLANE_OBJECT_ID0], D.id1 = (const uint32_t*)P[GK_PLANE_OBJECT_ID1], D.out = (uint2*)P[GK_PLANE_DENOISED];
+    D.W = (int)c.width, D.H = (int)c.height;
+    D.tiles = RowTiles{c.tileIndex, c.tileCount, c.tileRows};
+    {
+        const void* bufs[] = {P[GK_PLANE_DENOISED]};
+        waitAsyncCopyBeforeWriting(c, bufs, 1);
+    }
+    const dim3 block(TX, TY), grid((c.width + TX - 1) / TX, (c.height + TY - 1) / TY);
+    k_denoise_jbf<<<grid, block, 0, st>>>(c.dUbo, D);
+    GK_CUDA(cudaGetLastError());
+    c.stats.launches += 1;
+    c.tracedSinceFilter = false;
+    c.pendingHistorySwap = true;
+    return GK_OK;
+}
+
 void applyPendingHistorySwap(Context& c)
 {
     if (!c.pendingHistorySwap) return;

@@ -729,6 +729,7 @@ void freeFrameResources(Context& c)
 {
     if (c.asyncCopySrc) cudaEventSynchronize(c.evCopyDone), c.asyncCopySrc = nullptr;
     exchangeClosePeers(c); // the mapped peer planes belong to the extent being torn down
+    frameShardRelease(c);
     c.peers.myId0 = c.peers.myId1 = nullptr;
     for (void* p : c.pathAllocs) cudaFree(p);
     for (void* p : c.queueAllocs) cudaFree(p);
@@ -768,9 +769,9 @@ GkStatus allocFrameResources(Context& c)
     // owned rows of this rank's tile set
     uint32_t owned = 0;
     for (uint32_t r = 0; r < c.height; ++r)
-        if ((r / c.tileRows) % c.tileCount == c.tileIndex) ++owned;
+        if ((r / c.tileRows) % c.traceTileCount == c.traceTileIndex) ++owned;
     // paths are laid out in whole tile-row blocks so that pathToPixel stays arithmetic
-    const uint32_t blocks = (c.height + c.tileRows * c.tileCount - 1) / (c.tileRows * c.tileCount);
+    const uint32_t blocks = (c.height + c.tileRows * c.traceTileCount - 1) / (c.tileRows * c.traceTileCount);
     c.ownedRows = owned;
     c.pathCount = blocks * c.tileRows * c.width;
     const size_t n = c.pathCount;
@@ -859,7 +860,7 @@ GkStatus traceFrame(Context& c)
     }
     c.tracedSinceFilter = true;
     const uint32_t n = c.pathCount;
-    FrameParams P{c.width, c.height, c.tileIndex, c.tileCount, c.tileRows, n};
+    FrameParams P{c.width, c.height, c.traceTileIndex, c.traceTileCount, c.tileRows, n};
     const SceneView V = c.view();
     const ShadeScene SS = shadeSceneOf(c);
     const PlaneView PL = planeViewOf(c);

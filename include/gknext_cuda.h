@@ -52,7 +52,10 @@ typedef struct GkConfig {
 } GkConfig;
 
 enum GkConfigFlags {
-    GK_CFG_DEFAULT = 0
+    GK_CFG_DEFAULT = 0,
+    /* The path tracer covers the whole image although the context owns only its tile rows for the filters and the
+     * exchange: frame-sharded progressive rendering (gk_frame_shard_*), where every rank traces a different frame. */
+    GK_CFG_TRACE_ALL_ROWS = 1u << 0
 };
 
 /* Image planes, named after the reference's render targets
@@ -202,6 +205,22 @@ GkStatus gk_exchange_push(GkContext* ctx);
  *   gk_exchange_push_final    stores the owned rows of rtDenoised into rank `dst_rank` (-1: every peer). */
 GkStatus gk_filter_frame_owned(GkContext* ctx);
 GkStatus gk_exchange_push_final(GkContext* ctx, int dst_rank);
+
+/* Frame-sharded progressive rendering (ProgressiveRender != 0, BFSize == 0; contexts created with
+ * GK_CFG_TRACE_ALL_ROWS): in a super-step rank r traces the WHOLE frame number f0 + r (its own TotalFrames, i.e. its
+ * own random sequence); then every rank receives, for the rows it owns, the three source planes of all `world` frames
+ * and applies the progressive accumulation lerp(history, src_s, 1/TemporalFrames) for s = 0..world-1 in frame order
+ * (rounded to RGBA16F after every step, exactly what `world` consecutive single-GPU frames do), composes and tonemaps
+ * the last one.  gk_exchange_push_final then delivers the finished rows to the presenting rank.
+ *   gk_frame_shard_handle      allocates the gather buffer and writes its 64-byte CUDA IPC handle
+ *   gk_frame_shard_open        maps the gather buffers of all ranks (rank-major handles)
+ *   gk_frame_shard_push        one kernel: rows of this rank's frame go to the rank that owns them (NVLink stores)
+ *   gk_frame_shard_accumulate  the `world` lerps + compose on the owned rows
+ * The caller puts stream barriers between push and accumulate, as for gk_exchange_push. */
+GkStatus gk_frame_shard_handle(GkContext* ctx, void* out, size_t bytes);
+GkStatus gk_frame_shard_open(GkContext* ctx, const void* handles_all, uint32_t world);
+GkStatus gk_frame_shard_push(GkContext* ctx);
+GkStatus gk_frame_shard_accumulate(GkContext* ctx);
 
 /* Page-locked host memory for arrays that are uploaded every frame (the node proxies: the reference
  * writes them straight into a mapped device buffer, src/Assets/Scene.cpp:464-511).  Returns NULL when

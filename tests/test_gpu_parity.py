@@ -447,7 +447,7 @@ def test_two_gpu_tile_frame_equals_single_gpu_frame(built):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for mode, check, port in (("p2p", "temporal", 29531), ("nccl", "temporal", 29532), ("p2p", "progressive", 29533)):
+    for mode, check, port in (("p2p", "temporal", 29531), ("nccl", "temporal", 29532), ("p2p", "progressive", 29533), ("p2p", "frames", 29534)):
         env = dict(os.environ, GK_EXCHANGE=mode, GK_CHECK_MODE=check)
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
                               os.path.join(root, "tools", "multi_gpu_check.py")], env=env, capture_output=True, text=True, timeout=300)

@@ -20,12 +20,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     W, H, TR = 640, 360, 16
     eng = gk.Engine("room", 200000, 5)
-    progressive = os.environ.get("GK_CHECK_MODE", "temporal") == "progressive"
+    frames_mode = os.environ.get("GK_CHECK_MODE", "temporal") == "frames"
+    progressive = os.environ.get("GK_CHECK_MODE", "temporal") == "progressive" or frames_mode
     if progressive:  # the reference's benchmark state: per-pixel filters, only the final image is exchanged
         eng.set(TAA=0, NumberOfSamples=1, NumberOfBounces=4, Denoiser=0, ProgressiveRender=1)
     else:
         eng.set(TAA=1, NumberOfSamples=1, NumberOfBounces=4, Denoiser=1, TemporalFrames=8)
-    r = gk.Renderer(W, H, device=local, tile_index=rank, tile_count=world, tile_rows=TR)
+    r = gk.Renderer(W, H, device=local, tile_index=rank, tile_count=world, tile_rows=TR, trace_all_rows=frames_mode)
     eng.update_nodes()
     nodes, n = eng.update_nodes()  # steady-state proxies (second tick), shared by both contexts
     r.upload_scene(eng.scene_desc())
@@ -38,8 +39,30 @@ def main():
     mode = "nccl all-gather"
     if os.environ.get("GK_EXCHANGE", "p2p") == "p2p" and comp.enable_peer_exchange(r, rank, world):
         mode = "peer-to-peer push"
+    if frames_mode:
+        assert mode == "peer-to-peer push" and comp.enable_frame_sharding(r, rank, world)
+        mode = "frame-sharded: every rank traces its own frame, rows accumulate on their owners"
     ok = True
     for frame in range(4):
+        if frames_mode:
+            # super-step: rank k traces frame number frame*world + k of the single-GPU sequence
+            for k in range(world):
+                ubo_k = eng.ubo(W, H)
+                if k == rank:
+                    r.set_ubo(ubo_k)
+                    r.trace_frame()
+                if rank == 0:
+                    ref.set_ubo(ubo_k)
+                    ref.render_frame()
+                eng.advance_frame()
+            moved = comp.composite_frame_shard(r, rank, world, 0)
+            out = r.readback("DENOISED")
+            if rank == 0:
+                exp = ref.readback("DENOISED")
+                same = np.array_equal(out.view(np.uint16), exp.view(np.uint16))
+                print(f"super-step {frame} ({world} frames): multi-GPU == single-GPU final image: {same}, bytes exchanged per rank: {moved} ({mode})")
+                ok = ok and same
+            continue
         ubo = eng.ubo(W, H)
         r.set_ubo(ubo)
         r.trace_frame()
