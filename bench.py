@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="room", choices=list(WORKLOADS))
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "frames"],
+                    help="multi-GPU partition: image tiles of one frame (strong scaling) or, for progressive workloads without the denoiser, "
+                         "one whole frame per rank and step (a step is then `gpus` frames: weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -197,6 +200,10 @@ def main():
     eng.set(**settings)
     host = gk.host_lib()
     hr = host.gkh_renderer_create(eng.h, local_rank)
+    frame_shard = args.shard == "frames" and world > 1
+    if frame_shard:
+        assert settings.get("ProgressiveRender", 0) == 1 and settings.get("Denoiser", 1) == 0, "--shard frames needs a progressive workload without the denoiser (city, cornell)"
+        assert host.gkh_renderer_set_trace_all_rows(hr, 1) == 0
     assert host.gkh_renderer_set_tile(hr, rank, world, TILE_ROWS) == 0
 
     def chk(rc):
@@ -222,6 +229,13 @@ def main():
     if local_filters:
         exchange_mode = "filters on owned rows; final image rows pushed peer-to-peer over NVLink to rank 0 (the presenting rank) between two 4-byte all-reduce barriers"
 
+    if frame_shard:
+        assert exchange_mode.startswith("peer") or exchange_mode.startswith("filters"), "frame sharding needs the peer mapping"
+        assert comp.enable_frame_sharding(r, rank, world)
+        local_filters = False
+        exchange_mode = ("frame sharding: rank k traces the whole frame f0+k; rows of the three source planes go to their owning rank (NVLink stores), which "
+                         "accumulates the frames in order and composes; finished rows go to rank 0; three 4-byte all-reduce barriers per step")
+
     def frame(step_index, exchange=True):
         if dynamic:
             eng.step_scene(step_index)
@@ -230,11 +244,26 @@ def main():
             chk(host.gkh_renderer_render(hr))  # UBO fill + gk_set_ubo + gk_render_frame
             st = r.stats()
             return st.primaryRays + st.extensionRays + st.shadowRays, st.launches, st
-        ubo = eng.ubo(W, H)
+        if frame_shard:  # a step = `world` consecutive frames of the progressive sequence, one per rank
+            ubo = None
+            for k in range(world):
+                if k == rank:
+                    ubo = eng.ubo(W, H)
+                eng.advance_frame()
+        else:
+            ubo = eng.ubo(W, H)
         r.set_ubo(ubo)
         r.trace_frame()
         st = r.stats()
         rays, launches = st.primaryRays + st.extensionRays + st.shadowRays, st.launches
+        if frame_shard:
+            if exchange:
+                xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                xa.record(stream)
+                comp.composite_frame_shard(r, rank, world, 0)
+                xb.record(stream)
+                xchg_events.append((xa, xb))
+            return rays, launches + 4, st
         if local_filters:
             # progressive, no denoiser: per-pixel filters on the owned rows, then only the final image travels
             r.filter_frame_owned()
@@ -396,11 +425,12 @@ def main():
     line = {
         "metric": METRIC,
         "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
-        "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak" if frame_shard else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[args.workload], "width": W, "height": H, "spp": settings["NumberOfSamples"], "bounces": settings["NumberOfBounces"],
                    "triangles_instanced": int(info.instancedTriangles), "triangles_unique": int(info.triangleCount), "instances": int(info.instanceCount),
-                   "partition": f"{TILE_ROWS}-row tiles interleaved over {world} rank(s), scene+BVH replicated", "exchange": exchange_mode,
+                   "partition": (f"one whole frame per rank and step ({world} frames per step), rows owned in {TILE_ROWS}-row tiles for accumulation, scene+BVH replicated" if frame_shard
+                                 else f"{TILE_ROWS}-row tiles interleaved over {world} rank(s), scene+BVH replicated"), "exchange": exchange_mode,
                    "l2_policy": "per-frame working set (path state + queues + planes, >500 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
         "rays_per_step": round(total_rays / args.steps, 0), "gpu_launches": total_launches,
         "e2e": {"value": round(total_rays_e2e / (e2e_ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": int(h2d),

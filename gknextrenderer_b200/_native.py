@@ -192,6 +192,7 @@ HOST_API = {
     "gkh_screen_ray": (None, [_P, C.c_float, C.c_float, C.c_uint32, C.c_uint32, _P, _P]),
     "gkh_renderer_create": (_P, [_P, C.c_int]),
     "gkh_renderer_destroy": (None, [_P]),
+    "gkh_renderer_set_trace_all_rows": (C.c_int, [_P, C.c_int]),
     "gkh_renderer_set_tile": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),
     "gkh_renderer_create_swapchain": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "gkh_renderer_delete_swapchain": (C.c_int, [_P]),

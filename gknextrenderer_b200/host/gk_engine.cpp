@@ -117,6 +117,7 @@ void CudaPathTracingRenderer::CreateSwapChain(const VkExtent2D& extent)
     cfg.device = device_;
     cfg.width = extent.width, cfg.height = extent.height;
     cfg.tileIndex = tileIndex_, cfg.tileCount = tileCount_, cfg.tileRows = tileRows_;
+    cfg.flags = traceAllRows_ ? GK_CFG_TRACE_ALL_ROWS : GK_CFG_DEFAULT;
     check(gk_create(&cfg, &ctx_), "gk_create");
     extent_ = extent;
     instancesUploaded_ = false;

@@ -103,6 +103,7 @@ public:
     GkContext* Context() { return ctx_; }
     VkExtent2D Extent() const { return extent_; }
     void SetTile(uint32_t index, uint32_t count, uint32_t rows) { tileIndex_ = index, tileCount_ = count, tileRows_ = rows; }
+    void SetTraceAllRows(bool on) { traceAllRows_ = on; } // frame-sharded progressive rendering (GK_CFG_TRACE_ALL_ROWS)
 
 private:
     static void check(GkStatus s, const char* what)
@@ -113,6 +114,7 @@ private:
     VkExtent2D extent_{0, 0};
     int device_;
     uint32_t tileIndex_ = 0, tileCount_ = 1, tileRows_ = 16;
+    bool traceAllRows_ = false;
     bool instancesUploaded_ = false;
     size_t lastInstanceCount_ = 0;
     uint32_t updatesSinceRebuild_ = 0;

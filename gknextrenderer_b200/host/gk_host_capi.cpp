@@ -140,6 +140,7 @@ void gkh_screen_ray(void* h, float x, float y, uint32_t w, uint32_t hgt, float* 
 // ---- LogicRendererBase-shaped driver over the CUDA backend ----
 void* gkh_renderer_create(void* engine, int device) { return new HostRenderer(*(EngineMirror*)engine, device); }
 void gkh_renderer_destroy(void* r) { delete (HostRenderer*)r; }
+int gkh_renderer_set_trace_all_rows(void* r, int on) { GKH_TRY(((HostRenderer*)r)->r.SetTraceAllRows(on != 0)) }
 int gkh_renderer_set_tile(void* r, uint32_t index, uint32_t count, uint32_t rows) { GKH_TRY(((HostRenderer*)r)->r.SetTile(index, count, rows)) }
 int gkh_renderer_create_swapchain(void* r, uint32_t w, uint32_t h) { GKH_TRY(((HostRenderer*)r)->r.CreateSwapChain({w, h})) }
 int gkh_renderer_delete_swapchain(void* r) { GKH_TRY(((HostRenderer*)r)->r.DeleteSwapChain()) }
