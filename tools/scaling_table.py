@@ -9,13 +9,18 @@ for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench", "n*_*.json
     d = json.load(open(f))
     if d.get("impl") == "reference":
         continue
-    rows.setdefault(d["config"]["workload"].split(":")[0], {})[d["n_gpus"]] = d
+    mode = "frames" if d.get("scaling") == "weak" else "tiles"
+    rows.setdefault((d["config"]["workload"].split(":")[0], mode), {})[d["n_gpus"]] = d
 out = ["# Round 1: throughput and scaling on B200 (bench.py, 20 timed frames after 5 warm-up frames)\n",
        "`value` = rays traced by all ranks / max-over-ranks device time; `e2e` adds the UBO upload and the read-back of the final image on the presenting rank.",
        "Speed-ups are against the 1-GPU line of the same workload; the driver computes its own from the per-N values.\n"]
-for wl, by_n in rows.items():
-    base = by_n.get(1)
-    out.append(f"## {base['config']['workload'] if base else wl}\n")
+for (wl, mode), by_n in sorted(rows.items()):
+    base = by_n.get(1) or rows.get((wl, "tiles"), {}).get(1)
+    title = base['config']['workload'] if base else wl
+    if mode == "frames":
+        out.append(f"## {title} - FRAME-SHARDED (a step is N consecutive progressive frames, one per rank: weak scaling)\n")
+    else:
+        out.append(f"## {title} - image tiles of one frame (strong scaling)\n")
     out.append("| GPUs | Mrays/s | ms/frame | speed-up | e2e Mrays/s | trace per rank ms (min..max) | exchange ms | filters ms | tail ms | launches/frame |")
     out.append("|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|")
     for n in sorted(by_n):
@@ -27,7 +32,7 @@ for wl, by_n in rows.items():
         sp = f"{d['value'] / base['value']:.2f}x" if base else "-"
         out.append(f"| {n} | {d['value']:.0f} | {d['ms_per_step']:.2f} | {sp} | {d['e2e']['value']:.0f} | {trs} | {b.get('xchg', 0):.2f} | {b['rep'] + b['jbf']:.2f} | {b['tail']:.2f} | "
                    f"{d['gpu_launches'] / d['steps'] / n:.0f} |")
-    if base and base.get("cpu_baseline"):
+    if mode == "tiles" and base and base.get("cpu_baseline"):
         c = base["cpu_baseline"]
         out.append(f"\nCPU baseline on the same box: {c['value']:.1f} Mrays/s on {c['cores']} cores ({c['kind']}: {c['sample']}).")
     out.append("")
