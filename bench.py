@@ -404,6 +404,10 @@ def main():
                 "frac": round(achieved / l2_peak, 4) if l2_peak else None,
                 "traffic": traffic.get("dram_bytes_per_launch_avg") if args.workload == "room" and world == 1 else None,
                 "traffic_source": traffic.get("source") if args.workload == "room" and world == 1 else None,
+                "hbm": ({"bound": "hbm", "achieved": round(traffic["dram_bytes_per_wave_avg"] / (ext_ms / max(agg["ext_launches"], 1) * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(traffic["dram_bytes_per_wave_avg"] / (ext_ms / max(agg["ext_launches"], 1) * 1e-3) / 1e9 / hbm_peak, 4),
+                         "note": "measured DRAM bytes of the same launches against the HBM peak: the kernel is nowhere near the HBM bound, which is why the L2-level model is the reported roofline"}
+                        if args.workload == "room" and world == 1 and traffic.get("dram_bytes_per_wave_avg") and ext_ms > 0 else None),
                 "algorithmic_bytes_per_wave": round(bytes_per_ray * ext_rays / max(agg["ext_launches"], 1), 0),
                 "note": "achieved = L2-level algorithmic bytes (48 B ray/hit + 128 B per node visit + 48 B per triangle test, counted by an instrumented frame) / kernel time; "
                         "traffic = DRAM bytes per wave (its extend + shadow launch) from ncu: only the compulsory ~51 B/ray reach HBM, the node/triangle bytes are served by L1/L2 (SURVEY 8d: this kernel is L2/issue bound)",
