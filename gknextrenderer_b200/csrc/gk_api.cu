@@ -140,6 +140,7 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     if (const char* e = getenv("GK_CONCURRENT_SHADOW")) c.concurrentShadow = atoi(e) != 0;
     if (const char* e = getenv("GK_TRACE_BLOCK")) c.laneBlock = (unsigned)std::min(256, std::max(32, atoi(e) / 32 * 32));
     if (const char* e = getenv("GK_SHADE_BLOCKS")) c.shadeMinBlocks = atoi(e);
+    if (const char* e = getenv("GK_TIGHT_BOUNDS")) c.tightInstanceBounds = atoi(e) != 0;
     if (const char* e = getenv("GK_COST_TRI")) c.costTri = (float)atof(e);
     if (const char* e = getenv("GK_TLAS_PLOC")) c.tlasPloc = atoi(e) != 0;
     if (const char* e = getenv("GK_TLAS_PLOC_RADIUS")) c.tlasPlocRadius = std::min(256, std::max(1, atoi(e)));

@@ -692,6 +692,65 @@ __global__ void k_update_instances(const GkNodeProxy* __restrict__ nodes, uint32
     for (int k = 0; k < 5; ++k) o[k] = s[k];
 }
 
+// The world box of k_update_instances is the box of the eight transformed corners of the BLAS root box
+// (what tinybvh's BLASInstance::Update computes).  For a rotated instance it is much larger than the geometry
+// (a sphere's world box does not grow under rotation, its corner box does), and every ray that pierces the
+// slack pays a useless instance entry.  One warp per rotated instance folds the transformed triangle vertices
+// instead.  The TLAS is ours, so only conservativeness matters: the leaf box is padded by a whole quantisation
+// step of its parent node, orders of magnitude above the rounding of these transforms.
+__global__ void __launch_bounds__(256) k_tight_instance_bounds(const GkNodeProxy* __restrict__ nodes, uint32_t count, const ModelInfo* __restrict__ models, uint32_t modelCount,
+                                                               const InstRecord* __restrict__ inst, const TriRecord* __restrict__ tris, uint32_t maxTris,
+                                                               float4* __restrict__ plo, float4* __restrict__ phi)
+{
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (i >= count) return;
+    if (inst[i].blasRoot == kInvalid) return; // hidden / not ray traced
+    const GkNodeProxy& P = nodes[i];
+    const uint32_t model = P.modelId / 10;
+    if (model >= modelCount) return;
+    const ModelInfo& M = models[model];
+    if (M.triCount == 0 || M.triCount > maxTris) return;
+    float T[12]; // rows 0..2 of the row-major world matrix (glm column-major -> transposed)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) T[r * 4 + c] = P.worldTS[c * 4 + r];
+    // axis-aligned placement (each row of the 3x3 part has one non-zero): the corner box is already exact
+    bool aligned = true;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int nz = (T[r * 4] != 0.f) + (T[r * 4 + 1] != 0.f) + (T[r * 4 + 2] != 0.f);
+        aligned = aligned && nz <= 1;
+    }
+    if (aligned) return;
+    float lx = kFar, ly = kFar, lz = kFar, hx = -kFar, hy = -kFar, hz = -kFar;
+    // model m's triangles occupy [triOffset, triOffset + triCount) of the sorted records too (the model index leads the sort key)
+    const float4* tp = reinterpret_cast<const float4*>(tris + M.triOffset);
+    for (uint32_t t = lane; t < M.triCount; t += 32) {
+        const float4 a = __ldg(tp + 3 * t), b = __ldg(tp + 3 * t + 1), c = __ldg(tp + 3 * t + 2);
+        const float vx[3] = {a.x, a.x + b.x, a.x + c.x}, vy[3] = {a.y, a.y + b.y, a.y + c.y}, vz[3] = {a.z, a.z + b.z, a.z + c.z};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float wx = T[0] * vx[k] + T[1] * vy[k] + T[2] * vz[k] + T[3];
+            const float wy = T[4] * vx[k] + T[5] * vy[k] + T[6] * vz[k] + T[7];
+            const float wz = T[8] * vx[k] + T[9] * vy[k] + T[10] * vz[k] + T[11];
+            lx = fminf(lx, wx), ly = fminf(ly, wy), lz = fminf(lz, wz);
+            hx = fmaxf(hx, wx), hy = fmaxf(hy, wy), hz = fmaxf(hz, wz);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)), ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)), lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+        hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)), hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)), hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+    }
+    if (lane == 0) {
+        // never larger than the corner box, and a relative safety margin on top of the quantisation padding
+        const float4 clo = plo[i], chi = phi[i];
+        const float ex = 1e-5f * (hx - lx) + 1e-6f, ey = 1e-5f * (hy - ly) + 1e-6f, ez = 1e-5f * (hz - lz) + 1e-6f;
+        plo[i] = make_float4(fmaxf(clo.x, lx - ex), fmaxf(clo.y, ly - ey), fmaxf(clo.z, lz - ez), 0);
+        phi[i] = make_float4(fminf(chi.x, hx + ex), fminf(chi.y, hy + ey), fminf(chi.z, hz + ez), 0);
+    }
+}
+
 __global__ void k_model_bounds_from_groups(ModelInfo* models, uint32_t modelCount, const float4* glo, const float4* ghi, const uint32_t* rootRef)
 {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -923,6 +982,9 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
     GK_CUDA(T.phi.reserve(count));
     GK_CUDA(c.dInst.reserve(count));
     k_update_instances<<<gridFor(count, 128), 128, 0, st>>>(c.dNodes.p, count, c.dModels.p, (uint32_t)c.models.size(), c.dInst.p, T.plo.p, T.phi.p);
+    if (c.tightInstanceBounds)
+        k_tight_instance_bounds<<<gridFor((size_t)count * 32, 256), 256, 0, st>>>(c.dNodes.p, count, c.dModels.p, (uint32_t)c.models.size(), c.dInst.p, c.dTris.p,
+                                                                                 c.tightBoundsMaxTris, T.plo.p, T.phi.p);
     GkStatus s;
     GK_CUDA(c.dCounters.reserve(8));
     float* dArea = reinterpret_cast<float*>(c.dCounters.p + 4);

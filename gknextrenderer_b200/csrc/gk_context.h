@@ -191,6 +191,8 @@ struct Context {
     unsigned laneBlock = 256;       // threads (= rays) per block of the one-ray-per-lane trace kernel
     int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
     bool tlasPloc = true;           // PLOC topology for the TLAS (false: Karras radix tree)
+    bool tightInstanceBounds = true;     // world boxes of rotated instances from their transformed vertices (not the 8 corners of the BLAS box)
+    uint32_t tightBoundsMaxTris = 32768; // ... for models up to this many triangles
     float costTri = 0.3f;                // collapse cost model: one triangle test relative to one node visit
     int tlasPlocRadius = 64;             // search window of the nearest-neighbour pass
     uint32_t tlasPlocMax = 65536;        // ... up to this many instances (no gain measured on 200 k lattice bricks, 37 ms build)
