@@ -142,6 +142,8 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     if (const char* e = getenv("GK_SHADE_BLOCKS")) c.shadeMinBlocks = atoi(e);
     if (const char* e = getenv("GK_TIGHT_BOUNDS")) c.tightInstanceBounds = atoi(e) != 0;
     if (const char* e = getenv("GK_COST_TRI")) c.costTri = (float)atof(e);
+    if (const char* e = getenv("GK_BLAS_PLOC")) c.blasPloc = atoi(e) != 0;
+    if (const char* e = getenv("GK_BLAS_PLOC_RADIUS")) c.blasPlocRadius = std::min(256, std::max(1, atoi(e)));
     if (const char* e = getenv("GK_TLAS_PLOC")) c.tlasPloc = atoi(e) != 0;
     if (const char* e = getenv("GK_TLAS_PLOC_RADIUS")) c.tlasPlocRadius = std::min(256, std::max(1, atoi(e)));
     if (const char* e = getenv("GK_TLAS_SIZE_BITS")) c.tlasSizeBits = std::min(7, std::max(0, atoi(e)));
@@ -178,6 +180,7 @@ void gk_destroy(GkContext* ctx)
     c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release(), c.dRootRef.release();
     for (int k = 0; k < 2; ++k) c.dPlocRef[k].release(), c.dPlocLo[k].release(), c.dPlocHi[k].release();
     c.dPlocNn.release(), c.dPlocValid.release(), c.dPlocPos.release();
+    c.dPlocGrp[0].release(), c.dPlocGrp[1].release(), c.dPlocLeafGrp.release(), c.dPlocGroupBase.release();
     c.dCapture.release();
     for (cudaEvent_t e : c.evPool) cudaEventDestroy(e);
     if (c.evFork) cudaEventDestroy(c.evFork);

@@ -284,7 +284,7 @@ __global__ void k_ploc_init(uint32_t n, const float4* __restrict__ llo, const fl
     C.ref[i] = kLeafBit | i, C.lo[i] = llo[i], C.hi[i] = lhi[i];
 }
 
-__global__ void k_ploc_nearest(uint32_t m, PlocClusters C, uint32_t* __restrict__ nn, int radius)
+__global__ void k_ploc_nearest(uint32_t m, PlocClusters C, uint32_t* __restrict__ nn, int radius, const uint32_t* __restrict__ grp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int)m) return;
@@ -295,6 +295,7 @@ __global__ void k_ploc_nearest(uint32_t m, PlocClusters C, uint32_t* __restrict_
     const int j0 = max(0, i - radius), j1 = min((int)m - 1, i + radius);
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
+        if (grp && grp[j] != grp[i]) continue; // forest: clusters of different groups (models) never merge
         const float4 c = C.lo[j], d = C.hi[j];
         // an empty box (hidden instance: lo > hi) leaves the other box unchanged
         const float area = boxAreaOrZero(fminf(a.x, c.x), fminf(a.y, c.y), fminf(a.z, c.z), fmaxf(b.x, d.x), fmaxf(b.y, d.y), fmaxf(b.z, d.z));
@@ -335,13 +336,15 @@ __global__ void k_ploc_merge(uint32_t m, PlocClusters C, const uint32_t* __restr
     valid[i] = 1;
 }
 
-__global__ void k_ploc_compact(uint32_t m, PlocClusters in, PlocClusters out, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ pos, uint32_t* __restrict__ newCount)
+__global__ void k_ploc_compact(uint32_t m, PlocClusters in, PlocClusters out, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ pos, uint32_t* __restrict__ newCount,
+                               const uint32_t* __restrict__ grpIn, uint32_t* __restrict__ grpOut)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     if (valid[i]) {
         const uint32_t p = pos[i];
         out.ref[p] = in.ref[i], out.lo[p] = in.lo[i], out.hi[p] = in.hi[i];
+        if (grpIn) grpOut[p] = grpIn[i];
     }
     if (i == m - 1) *newCount = pos[i] + valid[i];
 }
@@ -351,6 +354,105 @@ __global__ void k_ploc_finish(PlocClusters C, uint32_t* __restrict__ parentI, ui
     const uint32_t r = C.ref[0];
     if (!(r & kLeafBit)) parentI[r] = kInvalid;
     *rootOut = r;
+}
+
+__global__ void k_ploc_groups(uint32_t n, const unsigned long long* __restrict__ keys, int shift, uint32_t* __restrict__ grp, uint32_t* __restrict__ groupBase)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = (uint32_t)(keys[i] >> shift);
+    grp[i] = g;
+    if (i == 0 || (uint32_t)(keys[i - 1] >> shift) != g) groupBase[g] = i; // groups are contiguous in the sorted order
+}
+
+__global__ void k_ploc_forest_finish(uint32_t m, PlocClusters C, uint32_t* __restrict__ parentI)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t r = C.ref[i];
+    if (!(r & kLeafBit)) parentI[r] = kInvalid; // root of its group
+}
+
+// A PLOC subtree does not cover a contiguous run of the Morton order, but BLAS leaves are runs of the
+// triangle array.  The leaves are therefore renumbered in depth-first order of the finished trees:
+// sizes bottom-up, position of a leaf = sum of the left-sibling sizes on its way up, then the key
+// range [first,last] of every node bottom-up again.
+__global__ void k_subtree_size(uint32_t n, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right, const uint32_t* __restrict__ parentI,
+                               const uint32_t* __restrict__ parentL, uint32_t* size, int* flags)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t cur = parentL[k];
+    while (cur != kInvalid) {
+        __threadfence();
+        if (atomicAdd(&flags[cur], 1) == 0) return;
+        const uint32_t L = left[cur], R = right[cur];
+        const volatile uint32_t* vs = size;
+        size[cur] = ((L & kLeafBit) ? 1u : vs[L]) + ((R & kLeafBit) ? 1u : vs[R]);
+        cur = parentI[cur];
+    }
+}
+
+__global__ void k_dfs_position(uint32_t n, const uint32_t* __restrict__ grp, const uint32_t* __restrict__ groupBase, const uint32_t* __restrict__ left,
+                               const uint32_t* __restrict__ right, const uint32_t* __restrict__ parentI, const uint32_t* __restrict__ parentL,
+                               const uint32_t* __restrict__ size, uint32_t* __restrict__ newPos)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t pos = 0, child = kLeafBit | k, cur = parentL[k];
+    while (cur != kInvalid) {
+        if (right[cur] == child) {
+            const uint32_t L = left[cur];
+            pos += (L & kLeafBit) ? 1u : size[L];
+        }
+        child = cur;
+        cur = parentI[cur];
+    }
+    newPos[k] = groupBase[grp[k]] + pos;
+}
+
+__global__ void k_dfs_permute(uint32_t n, const uint32_t* __restrict__ newPos, const uint32_t* __restrict__ order, const uint32_t* __restrict__ parentL,
+                              uint32_t* __restrict__ order2, uint32_t* __restrict__ parentL2)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t p = newPos[k];
+    order2[p] = order[k], parentL2[p] = parentL[k];
+}
+
+__global__ void k_dfs_fix_refs(uint32_t nodes, const uint32_t* __restrict__ newPos, uint32_t* __restrict__ left, uint32_t* __restrict__ right)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nodes) return;
+    const uint32_t L = left[i], R = right[i];
+    if (L & kLeafBit) left[i] = kLeafBit | newPos[L & 0x7fffffffu];
+    if (R & kLeafBit) right[i] = kLeafBit | newPos[R & 0x7fffffffu];
+}
+
+// internal-node slots PLOC did not use (one per group is spare) get an empty key range so that
+// k_group_roots never mistakes them for a root
+__global__ void k_mark_unused_nodes(uint32_t from, uint32_t to, uint32_t* __restrict__ first, uint32_t* __restrict__ last)
+{
+    const uint32_t i = from + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= to) return;
+    first[i] = 1u, last[i] = 0u;
+}
+
+__global__ void k_subtree_range(uint32_t n, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right, const uint32_t* __restrict__ parentI,
+                                const uint32_t* __restrict__ parentL, uint32_t* first, uint32_t* last, int* flags)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t cur = parentL[k];
+    while (cur != kInvalid) {
+        __threadfence();
+        if (atomicAdd(&flags[cur], 1) == 0) return;
+        const uint32_t L = left[cur], R = right[cur];
+        const volatile uint32_t *vf = first, *vl = last;
+        first[cur] = (L & kLeafBit) ? (L & 0x7fffffffu) : vf[L];
+        last[cur] = (R & kLeafBit) ? (R & 0x7fffffffu) : vl[R];
+        cur = parentI[cur];
+    }
 }
 
 // ------------------------------------------------------------------ per-group roots
@@ -833,7 +935,7 @@ static Bvh2View viewOf(const Lbvh& T)
 
 // Binary topology of T (left/right/parents) by PLOC over the Morton-sorted leaf boxes; the root reference
 // is left in c.dCounters[7].  keys/order must be in place (buildRadixTree without the radix tree).
-static GkStatus plocTopology(Context& c, Lbvh& T)
+static GkStatus plocTopology(Context& c, Lbvh& T, int radius, bool forest = false, uint32_t groups = 1, int groupShift = 42)
 {
     const uint32_t n = T.n;
     cudaStream_t st = c.stream;
@@ -846,6 +948,17 @@ static GkStatus plocTopology(Context& c, Lbvh& T)
     GK_CUDA(c.dPlocValid.reserve(n));
     GK_CUDA(c.dPlocPos.reserve(n));
     GK_CUDA(c.dCounters.reserve(8));
+    uint32_t *grpA = nullptr, *grpB = nullptr;
+    if (forest) {
+        GK_CUDA(c.dPlocGrp[0].reserve(n));
+        GK_CUDA(c.dPlocGrp[1].reserve(n));
+        GK_CUDA(c.dPlocLeafGrp.reserve(n));
+        GK_CUDA(c.dPlocGroupBase.reserve(groups));
+        GK_CUDA(cudaMemsetAsync(T.parentL.p, 0xff, sizeof(uint32_t) * n, st)); // a lone triangle of a model has no parent
+        k_ploc_groups<<<gridFor(n), 256, 0, st>>>(n, T.keys.p, groupShift, c.dPlocLeafGrp.p, c.dPlocGroupBase.p);
+        GK_CUDA(cudaMemcpyAsync(c.dPlocGrp[0].p, c.dPlocLeafGrp.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+        grpA = c.dPlocGrp[0].p, grpB = c.dPlocGrp[1].p;
+    }
     uint32_t* nodeCounter = c.dCounters.p + 5;
     uint32_t* newCount = c.dCounters.p + 6;
     uint32_t* rootOut = c.dCounters.p + 7;
@@ -862,22 +975,45 @@ static GkStatus plocTopology(Context& c, Lbvh& T)
             setLastError("PLOC did not converge");
             return GK_ERR_CUDA;
         }
-        k_ploc_nearest<<<gridFor(m), 256, 0, st>>>(m, A, c.dPlocNn.p, c.tlasPlocRadius);
+        k_ploc_nearest<<<gridFor(m), 256, 0, st>>>(m, A, c.dPlocNn.p, radius, grpA);
         k_ploc_merge<<<gridFor(m), 256, 0, st>>>(m, A, c.dPlocNn.p, c.dPlocValid.p, nodeCounter, T.left.p, T.right.p, T.parentI.p, T.parentL.p);
         size_t tb = c.dSortTemp.bytes();
         GK_CUDA(cub::DeviceScan::ExclusiveSum(c.dSortTemp.p, tb, c.dPlocValid.p, c.dPlocPos.p, (int)m, st));
-        k_ploc_compact<<<gridFor(m), 256, 0, st>>>(m, A, B, c.dPlocValid.p, c.dPlocPos.p, newCount);
+        k_ploc_compact<<<gridFor(m), 256, 0, st>>>(m, A, B, c.dPlocValid.p, c.dPlocPos.p, newCount, grpA, grpB);
         uint32_t next = 0;
         GK_CUDA(cudaMemcpyAsync(&next, newCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         GK_CUDA(cudaStreamSynchronize(st));
-        if (next >= m || next == 0) { // the globally closest pair is always mutual, so every round merges at least one pair
+        if (next == 0 || next > m || (next == m && !forest)) { // the globally closest pair is always mutual, so every round merges at least one pair
             setLastError("PLOC made no progress");
             return GK_ERR_CUDA;
         }
-        m = next;
         std::swap(A, B);
+        std::swap(grpA, grpB);
+        if (next == m) break; // forest: one cluster per group is left
+        m = next;
     }
-    k_ploc_finish<<<1, 1, 0, st>>>(A, T.parentI.p, rootOut);
+    if (!forest) {
+        k_ploc_finish<<<1, 1, 0, st>>>(A, T.parentI.p, rootOut);
+        GK_CUDA(cudaGetLastError());
+        return GK_OK;
+    }
+    k_ploc_forest_finish<<<gridFor(m), 256, 0, st>>>(m, A, T.parentI.p);
+    // ---- depth-first renumbering of the leaves (see k_subtree_size)
+    uint32_t nodesMade = 0;
+    GK_CUDA(cudaMemcpyAsync(&nodesMade, nodeCounter, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    GK_CUDA(cudaStreamSynchronize(st));
+    uint32_t* size = c.dPlocNn.p;      // scratch of the clustering, free now
+    uint32_t* newPos = c.dPlocValid.p;
+    GK_CUDA(cudaMemsetAsync(T.flags.p, 0, sizeof(int) * n, st));
+    k_subtree_size<<<gridFor(n), 256, 0, st>>>(n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, size, T.flags.p);
+    k_dfs_position<<<gridFor(n), 256, 0, st>>>(n, c.dPlocLeafGrp.p, c.dPlocGroupBase.p, T.left.p, T.right.p, T.parentI.p, T.parentL.p, size, newPos);
+    k_dfs_permute<<<gridFor(n), 256, 0, st>>>(n, newPos, T.order.p, T.parentL.p, T.orderAlt.p, c.dPlocPos.p);
+    if (nodesMade) k_dfs_fix_refs<<<gridFor(nodesMade), 256, 0, st>>>(nodesMade, newPos, T.left.p, T.right.p);
+    std::swap(T.order, T.orderAlt);
+    GK_CUDA(cudaMemcpyAsync(T.parentL.p, c.dPlocPos.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+    GK_CUDA(cudaMemsetAsync(T.flags.p, 0, sizeof(int) * n, st));
+    k_subtree_range<<<gridFor(n), 256, 0, st>>>(n, T.left.p, T.right.p, T.parentI.p, T.parentL.p, T.first.p, T.last.p, T.flags.p);
+    if (n >= 2 && nodesMade < n - 1) k_mark_unused_nodes<<<gridFor(n - 1 - nodesMade), 256, 0, st>>>(nodesMade, n - 1, T.first.p, T.last.p);
     GK_CUDA(cudaGetLastError());
     return GK_OK;
 }
@@ -938,8 +1074,13 @@ GkStatus buildBlasForest(Context& c)
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
-    GkStatus s = buildRadixTree(c, T, T.group.p, groups, 64);
+    const bool ploc = c.blasPloc && T.n > 2;
+    GkStatus s = buildRadixTree(c, T, T.group.p, groups, 64, 0, !ploc);
     if (s != GK_OK) return s;
+    if (ploc) {
+        s = plocTopology(c, T, c.blasPlocRadius, true, groups, 42);
+        if (s != GK_OK) return s;
+    }
     GK_CUDA(c.dTris.reserve(T.n));
     k_write_tri_records<<<gridFor(T.n), 256, 0, st>>>(sceneTriPositions().p, T.order.p, c.dModels.p, T.group.p, T.n, c.dTris.p);
     s = propagateBounds(c, T, c.sahCollapse, c.blasLeafMax, c.costTri);
@@ -1017,7 +1158,7 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
         if (ploc) {
             GK_CUDA(cudaMemsetAsync(T.first.p, 0, sizeof(uint32_t) * count, st));
             GK_CUDA(cudaMemsetAsync(T.last.p, 0, sizeof(uint32_t) * count, st));
-            s = plocTopology(c, T);
+            s = plocTopology(c, T, c.tlasPlocRadius);
             if (s != GK_OK) return s;
         }
         GK_CUDA(cudaMemsetAsync(dArea, 0, sizeof(float), st));

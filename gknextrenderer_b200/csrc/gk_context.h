@@ -190,6 +190,9 @@ struct Context {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     unsigned laneBlock = 256;       // threads (= rays) per block of the one-ray-per-lane trace kernel
     int shadeMinBlocks = 3;         // launch bound of k_shade (tuning hook)
+    bool blasPloc = false;          // PLOC topology (+ depth-first leaf renumbering) for the BLAS forest
+    int blasPlocRadius = 16;
+    DevBuf<uint32_t> dPlocGrp[2], dPlocLeafGrp, dPlocGroupBase;
     bool tlasPloc = true;           // PLOC topology for the TLAS (false: Karras radix tree)
     bool tightInstanceBounds = true;     // world boxes of rotated instances from their transformed vertices (not the 8 corners of the BLAS box)
     uint32_t tightBoundsMaxTris = 32768; // ... for models up to this many triangles
