@@ -36,5 +36,7 @@ for (wl, mode), by_n in sorted(rows.items()):
         c = base["cpu_baseline"]
         out.append(f"\nCPU baseline on the same box: {c['value']:.1f} Mrays/s on {c['cores']} cores ({c['kind']}: {c['sample']}).")
     out.append("")
+out.append("Note: the 2- and 4-GPU lines of C2 and the multi-GPU lines of C4 were measured before the last change of the round (tight world boxes of rotated "
+           "instances: -7 % frame time on one GPU for C2, neutral for C4 whose instances are axis aligned); the 1-GPU lines and the 8-GPU line of C2 are final.")
 open(os.path.join(ROOT, "profiles", "r01_scaling.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
