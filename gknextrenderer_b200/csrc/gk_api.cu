@@ -71,8 +71,9 @@ void waitAsyncCopyBeforeWriting(Context& c, const void* const* buffers, int coun
     if (!c.asyncCopySrc) return;
     for (int i = 0; i < count; ++i)
         if (buffers[i] == c.asyncCopySrc) {
+            // device-side ordering only: the copy stays "in flight" for the host until gk_readback_wait
+            // (or the next gk_readback_async) has synchronised with it
             cudaStreamWaitEvent(c.stream, c.evCopyDone, 0);
-            c.asyncCopySrc = nullptr; // everything later on the stream is ordered behind the copy
             return;
         }
 }
