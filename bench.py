@@ -35,6 +35,8 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # name: (scene, scene args, width, height, settings)
     "room": ("room", (1000000, 1234), 1920, 1080, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
+    # the same room with unique geometry: 413 objects, each its own model / BLAS, nothing instanced (50 MB of triangle records + BVH)
+    "roomu": ("roomu", (1000000, 1234), 1920, 1080, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
     "cornell": ("cornell", (), 640, 360, dict(NumberOfSamples=8, NumberOfBounces=4, TemporalFrames=16, Denoiser=0, TAA=0, ProgressiveRender=1)),
     "bricks": ("bricks", (200000, 42), 1920, 1080, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
     # progressive accumulation, denoiser off: the state gkNextBenchmark runs in (gkNextBenchmark.cpp:16-31); one step = 1 of the 64 spp
@@ -42,6 +44,7 @@ WORKLOADS = {
 }
 WORKLOAD_NAMES = {
     "room": "C2: procedural 1M-triangle room (1280 instances of 6 meshes), 1920x1080, 1 spp, 4 bounces, sun+sky, reproject + JBF",
+    "roomu": "C2u: procedural 1M-UNIQUE-triangle room (413 objects, one BLAS each, no instancing), 1920x1080, 1 spp, 4 bounces, sun+sky, reproject + JBF",
     "cornell": "C1: built-in Cornell box, 640x360, 8 spp, 4 bounces",
     "bricks": "C3: 200k instanced bricks, per-frame TLAS refit, 1920x1080, 1 spp, 4 bounces",
     "city": "C4: 10M-triangle instanced city, 3840x2160, progressive (1 of 64 spp per step), 4 bounces, denoiser off",
@@ -421,9 +424,9 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
 
     # ---- CPU baseline: the reference's tinybvh on the rays the GPU traced (bounded sample)
-    cpu = None
+    cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_baseline(eng, r, frame, W, H)
+        cpu, parity = cpu_baseline(eng, r, frame, W, H)
 
     value = total_rays / (dev_ms * 1e-3) / 1e6
     line = {
@@ -445,7 +448,7 @@ def main():
         "host_gap_ms_per_step": round((wall_ms - dev_ms) / args.steps, 4),
         "bvh": {"blas_build_ms": round(info.msBlasBuild, 3), "tlas_build_ms": round(info.msTlasBuild, 3), "tlas_refit_ms": round(info.msRefit, 3), "refits_rejected": int(r.bvh_info().refitsRejected),
                 "wide_nodes_blas": int(info.blasNodes8), "wide_nodes_tlas": int(info.tlasNodes8), "bytes": int(info.bytesBvh + info.bytesGeometry)},
-        "roofline": roofline, "roofline_filters": roofline_filters, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "roofline_filters": roofline_filters, "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
     }
     print(json.dumps(line))
     r.h = None  # the context belongs to the host renderer
@@ -472,24 +475,46 @@ def _cpu_rate(eng, rays_list, repeats=3):
     use_ref = ol.have_ref()
     scene = ol.OracleScene(eng.scene_desc(), nodes, n, use_ref=use_ref)
     threads = os.cpu_count() or 1
-    res = []
+    res, hits = [], []
     for rays in rays_list:
         best = None
         for _ in range(repeats):
-            scene.intersect(rays, threads=threads)
+            tuv, ids = scene.intersect(rays, threads=threads)
             best = scene.last_seconds if best is None else min(best, scene.last_seconds)
         res.append((len(rays), best))
-    return use_ref, threads, res
+        hits.append((tuv, ids))
+    return use_ref, threads, res, hits
+
+
+TIE_EPS = 2.0 ** -21
+
+
+def hit_parity(gpu_hits, cpu_hits):
+    """GPU hit records against the CPU reference's on the same rays (the classification of tests/test_gpu_parity.py):
+    ids equal + t/u/v bit-equal, exact-distance ties (different id, same t bits), epsilon ties (coplanar surfaces: the GPU
+    distance is not farther and within 2^-21 relative), errors (anything else)."""
+    tot = dict(rays=0, id_equal=0, tuv_bit_equal=0, exact_t_ties=0, eps_ties=0, errors=0)
+    for (g_tuv, g_ids), (o_tuv, o_ids) in zip(gpu_hits, cpu_hits):
+        differ = (g_ids != o_ids).any(axis=1)
+        gb, ob = np.ascontiguousarray(g_tuv).view(np.uint32), np.ascontiguousarray(o_tuv).view(np.uint32)
+        tg, to = g_tuv[:, 0].astype(np.float64), o_tuv[:, 0].astype(np.float64)
+        exact = differ & (gb[:, 0] == ob[:, 0])
+        eps = differ & ~exact & (np.abs(tg - to) <= TIE_EPS * np.maximum(np.abs(tg), np.abs(to))) & (tg <= to)
+        tot["rays"] += len(g_ids); tot["id_equal"] += int((~differ).sum()); tot["tuv_bit_equal"] += int(((gb == ob).all(axis=1) & ~differ).sum())
+        tot["exact_t_ties"] += int(exact.sum()); tot["eps_ties"] += int(eps.sum()); tot["errors"] += int((differ & ~exact & ~eps).sum())
+    return tot
 
 
 def cpu_baseline(eng, r, frame_fn, W, H):
     rays_list = _captured_sample(eng, r, frame_fn)
-    use_ref, threads, res = _cpu_rate(eng, rays_list)
+    use_ref, threads, res, cpu_hits = _cpu_rate(eng, rays_list)
     total = sum(n for n, _ in res)
     secs = sum(s for _, s in res)
+    parity = hit_parity([r.intersect(rays) for rays in rays_list], cpu_hits)  # the GPU traversal on the very same ray buffers (checker only, untimed)
+    parity["against"] = "real tinybvh (oracle/_ref)" if use_ref else "oracle port"
     return {"value": round(total / secs / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": "reference" if use_ref else "port",
             "sample": f"{res[0][0]} primary rays ({res[0][0] / res[0][1] / 1e6:.2f} Mrays/s) + {res[1][0]} third-wave bounce rays ({res[1][0] / max(res[1][1], 1e-9) / 1e6:.2f} Mrays/s) "
-                      "captured from the GPU frame, traversal only, best of 3, tinybvh BVH::Intersect over the TLAS" + ("" if use_ref else " (oracle port)")}
+                      "captured from the GPU frame, traversal only, best of 3, tinybvh BVH::Intersect over the TLAS" + ("" if use_ref else " (oracle port)")}, parity
 
 
 def reference_arm(args, scene_name, scene_args, W, H, settings):

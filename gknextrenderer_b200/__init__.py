@@ -202,6 +202,10 @@ class Renderer:
         self._check(self.lib.gk_get_bvh_info(self.h, C.byref(s)))
         return s
 
+    def set_option(self, name: str, value: float):
+        """Tuning hook (gk_set_option): e.g. trace_variant, sched_refill_min, coop_threshold."""
+        self._check(self.lib.gk_set_option(self.h, name.encode(), float(value)))
+
     def set_traversal_stats(self, on: bool):
         self._check(self.lib.gk_set_traversal_stats(self.h, 1 if on else 0))
 

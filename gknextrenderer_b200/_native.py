@@ -116,7 +116,9 @@ class GkFrameStats(C.Structure):
                 ("msShade", C.c_float), ("msShadow", C.c_float), ("msAccumulate", C.c_float), ("msReproject", C.c_float),
                 ("msDenoise", C.c_float), ("nodeVisits", C.c_uint64), ("triTests", C.c_uint64),
                 ("tlasVisits", C.c_uint64), ("instanceEntries", C.c_uint64), ("msTail", C.c_float), ("tailPaths", C.c_uint32),
-                ("tailExtensionRays", C.c_uint64), ("tailShadowRays", C.c_uint64), ("maxStack", C.c_uint32), ("msTrace", C.c_float)]
+                ("tailExtensionRays", C.c_uint64), ("tailShadowRays", C.c_uint64), ("maxStack", C.c_uint32), ("msTrace", C.c_float),
+                ("schedIters", C.c_uint64 * 3), ("schedLanes", C.c_uint64 * 3), ("schedRefills", C.c_uint64), ("schedRefillLanes", C.c_uint64),
+                ("schedPopIters", C.c_uint64), ("schedPopLanes", C.c_uint64)]
 
 
 class GkBvhInfo(C.Structure):
@@ -168,6 +170,7 @@ CUDA_API = {
     "gk_synchronize": (C.c_int, [_P]),
     "gk_get_stats": (C.c_int, [_P, C.POINTER(GkFrameStats)]),
     "gk_get_bvh_info": (C.c_int, [_P, C.POINTER(GkBvhInfo)]),
+    "gk_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "gk_set_traversal_stats": (C.c_int, [_P, C.c_int]),
     "gk_stream": (_P, [_P]),
     "gk_set_ray_capture": (C.c_int, [_P, C.c_int]),

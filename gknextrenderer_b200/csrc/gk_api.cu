@@ -152,6 +152,10 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     if (const char* e = getenv("GK_TAIL_FRACTION")) c.tailFraction = (float)atof(e);
     if (const char* e = getenv("GK_TAIL_THRESHOLD")) c.tailThreshold = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("GK_COOP_THRESHOLD")) c.coopThreshold = (uint32_t)strtoul(e, nullptr, 10); // tuning / test hook
+    if (const char* e = getenv("GK_TRACE_VARIANT")) c.traceVariant = atoi(e);
+    if (const char* e = getenv("GK_SCHED_REFILL_MIN")) c.schedRefillMin = (uint32_t)std::min(32, std::max(1, atoi(e)));
+    if (const char* e = getenv("GK_SCHED_BIAS_NODE")) c.schedBiasN = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("GK_SCHED_MIN_RAYS")) c.schedMinRays = (uint32_t)strtoul(e, nullptr, 10);
     if (c.tileIndex >= c.tileCount) {
         delete h;
         setLastError("gk_create: tileIndex >= tileCount");
@@ -323,7 +327,7 @@ GkStatus gk_intersect(GkContext* ctx, const float* rays, uint32_t count, float* 
     if (s == GK_OK) {
         if (out_tuv) GK_CUDA(cudaMemcpyAsync(out_tuv, dt.p, 12 * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
         if (out_ids) GK_CUDA(cudaMemcpyAsync(out_ids, di.p, 8 * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
-        GK_CUDA(cudaStreamSynchronize(c.stream));
+        s = checkTraversalOverflow(c);
     }
     dr.release(), dt.release(), di.release();
     return s;
@@ -357,7 +361,7 @@ GkStatus gk_raycast(GkContext* ctx, const float* origin_dir, uint32_t count, GkR
         k_raycast_results<<<(count + 255) / 256, 256, 0, c.stream>>>(dod.p, dt.p, di.p, count, c.dNodes.p, c.dModels.p, c.dFaceNormals.p, dres.p);
         GK_CUDA(cudaGetLastError());
         GK_CUDA(cudaMemcpyAsync(out, dres.p, sizeof(GkRayCastResult) * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
-        GK_CUDA(cudaStreamSynchronize(c.stream));
+        s = checkTraversalOverflow(c);
     }
     dod.release(), dr.release(), dt.release(), di.release(), dres.release();
     return s;
@@ -555,6 +559,27 @@ GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out)
     out->bytesBvh = (uint64_t)(c.blasNodeCount + c.tlasNodeCount) * sizeof(WideNode) + (uint64_t)c.nodeCount * sizeof(InstRecord);
     out->msBlasBuild = c.msBlasBuild, out->msTlasBuild = c.msTlasBuild, out->msRefit = c.msRefit;
     out->refitsRejected = c.refitRejected, out->tlasAreaAtBuild = c.tlasAreaAtBuild;
+    return GK_OK;
+}
+
+GkStatus gk_set_option(GkContext* ctx, const char* name, double value)
+{
+    GK_CHECK_CTX(ctx);
+    if (!name) return GK_ERR_INVALID_ARGUMENT;
+    const std::string n(name);
+    if (n == "trace_variant") c.traceVariant = (int)value;
+    else if (n == "sched_refill_min") c.schedRefillMin = (uint32_t)std::min(32.0, std::max(1.0, value));
+    else if (n == "sched_bias_node") c.schedBiasN = (uint32_t)std::max(0.0, value);
+    else if (n == "sched_min_rays") c.schedMinRays = (uint32_t)std::max(0.0, value);
+    else if (n == "coop_threshold") c.coopThreshold = (uint32_t)std::max(0.0, value);
+    else if (n == "tail_threshold") c.tailThreshold = (uint32_t)std::max(0.0, value);
+    else if (n == "tail_fraction") c.tailFraction = (float)value;
+    else if (n == "concurrent_shadow") c.concurrentShadow = value != 0;
+    else if (n == "wave_lookahead") c.waveLookahead = (uint32_t)std::max(0.0, value);
+    else {
+        setLastError("gk_set_option: unknown option '" + n + "'");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
     return GK_OK;
 }
 

@@ -204,6 +204,18 @@ struct Context {
     DevBuf<float4> dPlocLo[2], dPlocHi[2];
     int tlasSizeBits = 2;           // extended Morton code of the TLAS: box-size bits woven into the key (0 = plain Morton)
     bool sahCollapse = true;        // cost-driven wide collapse (false: greedy by surface area)
+    // scheduled traversal kernel (gk_trace_sched.cuh)
+    int traceVariant = 1;            // 0: while-while lane kernel / cooperative kernel, 1: persistent vote-scheduled kernel
+    uint32_t schedRefillMin = 8;     // refill a warp's idle lanes once this many rays have finished
+    uint32_t schedBiasN = 0;         // vote bias towards the node step (lanes)
+    uint32_t schedMinRays = 0;       // waves smaller than this keep the variant-0 kernels
+    int schedBlocksPerSm = 0, smCount = 0;
+    static constexpr uint32_t kCursorCount = 1024;
+    uint32_t* dCursors = nullptr;    // one zeroed queue cursor per launch of a frame
+    uint32_t cursorNext = 0;
+    struct SchedStats* dSchedStats = nullptr;
+    uint32_t* dOverflow = nullptr;   // set by a traversal that had to drop a stack entry
+    uint32_t waveLookahead = 4;      // waves the host may run ahead of the device in the wave loop
     DevBuf<float4> dCapture;
     uint32_t capturedCount = 0;
     uint64_t frameIndex = 0;
@@ -213,7 +225,7 @@ struct Context {
     {
         SceneView v;
         v.tlasNodes = dTlasNodes.p, v.blasNodes = dBlasNodes.p, v.tris = dTris.p, v.inst = dInst.p;
-        v.tlasRoot = tlasRoot, v.instanceCount = nodeCount;
+        v.tlasRoot = tlasRoot, v.instanceCount = nodeCount, v.overflowFlag = dOverflow;
         return v;
     }
 };
@@ -228,6 +240,7 @@ GkStatus allocFrameResources(Context& c);
 void freeFrameResources(Context& c);
 GkStatus traceFrame(Context& c);
 GkStatus intersectDevice(Context& c, const float4* rays, uint32_t n, float* tuv, uint32_t* ids, bool anyHit);
+GkStatus checkTraversalOverflow(Context& c); // synchronises; GK_ERR_UNSUPPORTED if a traversal dropped a stack entry
 GkStatus raycastBatch(Context& c, const float* originDir, uint32_t n, GkRayCastResult* out);
 // gk_filters.cu
 GkStatus filterFrame(Context& c);

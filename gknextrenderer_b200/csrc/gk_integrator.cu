@@ -21,9 +21,7 @@
 // per ray.  All kernels are one thread per queue entry, 256 threads per block.
 #include "gk_context.h"
 #include "gk_shading.cuh"
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
+#include "gk_trace_sched.cuh"
 
 namespace gk {
 
@@ -189,6 +187,17 @@ __global__ void __launch_bounds__(256, kCoop ? 2 : 4) k_trace(SceneView V, RayIO
             atomicMax(&stats->maxStack, local.maxStack);
         }
     }
+}
+
+// The scheduled (persistent, vote-driven) traversal kernel: gk_trace_sched.cuh.  `countPtr` (device) overrides
+// `countImm` so that a wave can be launched before the host knows its size.
+template <bool kAnyHit, bool kStats, class RayIO>
+__global__ void __launch_bounds__(kSchedBlock, 4) k_trace_sched(SceneView V, RayIO io, const uint32_t* __restrict__ countPtr, uint32_t countImm, uint32_t* __restrict__ cursor,
+                                                              SchedParams prm, TraversalStats* stats, SchedStats* sched)
+{
+    __shared__ uint32_t sStack[2 * kSmemStack * kSchedBlock];
+    const uint32_t count = countPtr ? *countPtr : countImm;
+    traverseScheduled<kAnyHit, kStats, RayIO>(V, io, count, cursor, prm, sStack, stats, sched);
 }
 
 // -------------------------------------------------------------------------------- shade
@@ -659,6 +668,7 @@ __global__ void __launch_bounds__(128, 4) k_tail(const GkUniformBufferObject* __
             kind = e.kind;
             r.o = make_float4(e.o.x, e.o.y, e.o.z, e.tmin), r.d = make_float4(e.d.x, e.d.y, e.d.z, e.tmax);
         }
+        if (kind != 0) counters[2] = 1ull; // the step guard expired with the path still alive: the host reports it
     }
     const unsigned full = 0xffffffffu;
     for (int o = 16; o; o >>= 1) nE += __shfl_xor_sync(full, nE, o), nS += __shfl_xor_sync(full, nS, o);
@@ -692,10 +702,44 @@ static void launchMapped(cudaStream_t st, unsigned grid, unsigned block, const S
     else k_trace<kAnyHit, kCoop, false, RayIO><<<grid, block, 0, st>>>(V, io, count, ts);
 }
 
+// Next zeroed fetch cursor of the frame (the block of cursors is cleared once per frame / per intersect call).
+static uint32_t* nextCursor(Context& c, cudaStream_t)
+{
+    if (c.cursorNext >= Context::kCursorCount) { // more launches than cursors since the last clear (frames with hundreds of waves): drain and clear
+        cudaStreamSynchronize(c.stream);
+        if (c.stream2) cudaStreamSynchronize(c.stream2);
+        cudaMemsetAsync(c.dCursors, 0, sizeof(uint32_t) * Context::kCursorCount, c.stream);
+        cudaStreamSynchronize(c.stream);
+        c.cursorNext = 0;
+    }
+    return c.dCursors + c.cursorNext++;
+}
+
+template <bool kAnyHit, class RayIO>
+static void launchSched(Context& c, const SceneView& V, const RayIO& io, uint32_t count, cudaStream_t stream)
+{
+    if (c.schedBlocksPerSm == 0) {
+        int nb = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_sched<false, false, QueueIO>, kSchedBlock, 0);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+        c.schedBlocksPerSm = nb > 0 ? nb : 1, c.smCount = sms > 0 ? sms : 1;
+    }
+    const unsigned resident = (unsigned)(c.schedBlocksPerSm * c.smCount);
+    const unsigned grid = std::max(1u, std::min(resident, (count + kSchedBlock - 1) / kSchedBlock));
+    const SchedParams prm{std::min(32u, std::max(1u, c.schedRefillMin)), c.schedBiasN};
+    uint32_t* cursor = nextCursor(c, stream);
+    if (c.travStats) k_trace_sched<kAnyHit, true, RayIO><<<grid, kSchedBlock, 0, stream>>>(V, io, nullptr, count, cursor, prm, c.dTravStats, c.dSchedStats);
+    else k_trace_sched<kAnyHit, false, RayIO><<<grid, kSchedBlock, 0, stream>>>(V, io, nullptr, count, cursor, prm, nullptr, nullptr);
+}
+
 template <bool kAnyHit, class RayIO>
 static void launchTraceIO(Context& c, const SceneView& V, const RayIO& io, uint32_t count, cudaStream_t stream = nullptr)
 {
     if (!stream) stream = c.stream;
+    if (c.traceVariant == 1 && count >= c.schedMinRays) {
+        launchSched<kAnyHit>(c, V, io, count, stream);
+        return;
+    }
     const bool coop = count < c.coopThreshold;
     const unsigned per = coop ? kRaysPerBlock : c.laneBlock; // rays per block
     const unsigned grid = (count + per - 1) / per;
@@ -746,6 +790,12 @@ void freeFrameResources(Context& c)
     c.dTravStats = nullptr;
     if (c.dTailCounters) cudaFree(c.dTailCounters);
     c.dTailCounters = nullptr;
+    if (c.dCursors) cudaFree(c.dCursors);
+    c.dCursors = nullptr;
+    if (c.dSchedStats) cudaFree(c.dSchedStats);
+    c.dSchedStats = nullptr;
+    if (c.dOverflow) cudaFree(c.dOverflow);
+    c.dOverflow = nullptr;
 }
 
 static size_t planePixelBytes(int plane)
@@ -806,9 +856,16 @@ GkStatus allocFrameResources(Context& c)
     }
     GK_CUDA(cudaMalloc(&c.dUbo, sizeof(GkUniformBufferObject)));
     GK_CUDA(cudaMallocHost(&c.hCounts, 64));
-    GK_CUDA(cudaMalloc(&c.dTailCounters, 2 * sizeof(unsigned long long)));
+    GK_CUDA(cudaMalloc(&c.dTailCounters, 3 * sizeof(unsigned long long)));
     GK_CUDA(cudaMalloc(&c.dTravStats, sizeof(TraversalStats)));
     GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), c.stream));
+    GK_CUDA(cudaMalloc(&c.dCursors, sizeof(uint32_t) * Context::kCursorCount));
+    GK_CUDA(cudaMemsetAsync(c.dCursors, 0, sizeof(uint32_t) * Context::kCursorCount, c.stream));
+    c.cursorNext = 0;
+    GK_CUDA(cudaMalloc(&c.dSchedStats, sizeof(SchedStats)));
+    GK_CUDA(cudaMemsetAsync(c.dSchedStats, 0, sizeof(SchedStats), c.stream));
+    GK_CUDA(cudaMalloc(&c.dOverflow, sizeof(uint32_t)));
+    GK_CUDA(cudaMemsetAsync(c.dOverflow, 0, sizeof(uint32_t), c.stream));
     GK_CUDA(cudaStreamSynchronize(c.stream));
     return GK_OK;
 }
@@ -880,7 +937,14 @@ GkStatus traceFrame(Context& c)
     }
 
     GK_CUDA(cudaMemcpyAsync(c.dUbo, &c.ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, st));
-    if (c.travStats) GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), st));
+    if (c.travStats) {
+        GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), st));
+        GK_CUDA(cudaMemsetAsync(c.dSchedStats, 0, sizeof(SchedStats), st));
+    }
+    if (c.cursorNext) { // queue cursors of the previous frame's launches
+        GK_CUDA(cudaMemsetAsync(c.dCursors, 0, sizeof(uint32_t) * c.cursorNext, st));
+        c.cursorNext = 0;
+    }
     const size_t evStart = mark();
     int cur = 0;
     k_generate<<<gridFor(n), 256, 0, st>>>(c.dUbo, P, c.paths, c.extendQ[cur]);
@@ -901,12 +965,12 @@ GkStatus traceFrame(Context& c)
         if (wave > 0 && countE + countS <= tailLimit && !c.travStats && c.captureWave < 0) {
             // few paths left: finish them in one launch
             const size_t a = mark();
-            GK_CUDA(cudaMemsetAsync(c.dTailCounters, 0, 2 * sizeof(unsigned long long), st));
+            GK_CUDA(cudaMemsetAsync(c.dTailCounters, 0, 3 * sizeof(unsigned long long), st));
             k_tail<<<gridFor((size_t)countE + countS, 128), 128, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.dTailCounters);
             fs.launches++;
             const size_t b = mark();
             spans.push_back({a, b, 5});
-            GK_CUDA(cudaMemcpyAsync(c.hCounts + 2, c.dTailCounters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            GK_CUDA(cudaMemcpyAsync(c.hCounts + 2, c.dTailCounters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             fs.tailPaths = countE + countS;
             tailRan = true;
             fs.waves++;
@@ -976,12 +1040,20 @@ GkStatus traceFrame(Context& c)
         fs.waves++;
         cur = nxt;
     }
+    if (!tailRan && (countE || countS)) {
+        // the wave limit was hit with paths still alive (NumberOfSamples x bounces far beyond what a frame is): never
+        // accumulate unfinished paths
+        GK_CUDA(cudaStreamSynchronize(st));
+        setLastError("gk_trace_frame: " + std::to_string(countE + countS) + " paths were still alive after the wave limit (4096); lower NumberOfSamples / bounces");
+        return GK_ERR_UNSUPPORTED;
+    }
     const size_t g = mark();
     k_accumulate<<<gridFor(n), 256, 0, st>>>(P, c.paths, PL);
     fs.launches++;
     const size_t hEnd = mark();
     spans.push_back({g, hEnd, 4});
     GK_CUDA(cudaGetLastError());
+    GK_CUDA(cudaMemcpyAsync(c.hCounts + 12, c.dOverflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st)); // traversal stack overflow flag
     GK_CUDA(cudaStreamSynchronize(st));
     for (const Span& s : spans) {
         float ms = 0;
@@ -996,8 +1068,12 @@ GkStatus traceFrame(Context& c)
     }
     cudaEventElapsedTime(&fs.msTotal, c.evPool[evStart], c.evPool[hEnd]);
     if (tailRan) {
-        unsigned long long t[2];
+        unsigned long long t[3];
         memcpy(t, c.hCounts + 2, sizeof(t));
+        if (t[2]) {
+            setLastError("gk_trace_frame: paths were still alive when the tail kernel's step guard (65536) expired; lower NumberOfSamples / bounces");
+            return GK_ERR_UNSUPPORTED;
+        }
         fs.extensionRays += t[0], fs.shadowRays += t[1];
         fs.tailExtensionRays = t[0], fs.tailShadowRays = t[1];
     }
@@ -1005,6 +1081,29 @@ GkStatus traceFrame(Context& c)
         TraversalStats h;
         GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));
         fs.nodeVisits = h.nodeVisits, fs.triTests = h.triTests, fs.tlasVisits = h.tlasVisits, fs.instanceEntries = h.instanceEntries, fs.maxStack = (uint32_t)h.maxStack;
+        SchedStats ss;
+        GK_CUDA(cudaMemcpy(&ss, c.dSchedStats, sizeof(ss), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 3; ++k) fs.schedIters[k] = ss.iters[k], fs.schedLanes[k] = ss.lanes[k];
+        fs.schedRefills = ss.refills, fs.schedRefillLanes = ss.refillLanes, fs.schedPopIters = ss.popIters, fs.schedPopLanes = ss.popLanes;
+    }
+    if (c.hCounts[12]) {
+        c.hCounts[12] = 0;
+        return checkTraversalOverflow(c);
+    }
+    return GK_OK;
+}
+
+// A traversal that ran out of stack (GK_TRAVERSAL_STACK entries) dropped an entry and may have missed a hit: that is an
+// error of the call, not a statistic.  The flag costs one 4-byte read-back per frame / intersect call.
+GkStatus checkTraversalOverflow(Context& c)
+{
+    uint32_t flag = 0;
+    GK_CUDA(cudaMemcpyAsync(&flag, c.dOverflow, sizeof(flag), cudaMemcpyDeviceToHost, c.stream));
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    if (flag) {
+        GK_CUDA(cudaMemsetAsync(c.dOverflow, 0, sizeof(uint32_t), c.stream));
+        setLastError("traversal stack overflow: the scene needs more than GK_TRAVERSAL_STACK (" + std::to_string(kStackSize) + ") entries for some ray; hits may be missing");
+        return GK_ERR_UNSUPPORTED;
     }
     return GK_OK;
 }

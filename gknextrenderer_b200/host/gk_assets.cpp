@@ -435,6 +435,52 @@ void ProceduralRoom(Scene& scene, uint32_t targetTriangles, uint32_t seed)
     }
 }
 
+// The same room with UNIQUE geometry: every object is its own model (its own BLAS), nothing is instanced, so the
+// 1 M triangles are 1 M distinct triangle records (~50 MB of geometry + BVH) instead of six meshes that live in L1.
+// Kitchen / LivingRoom-class: the reference's gallery scenes are single-use meshes (assets/models, not in this tree).
+void ProceduralRoomUnique(Scene& scene, uint32_t targetTriangles, uint32_t seed)
+{
+    std::mt19937 rng(seed);
+    std::uniform_real_distribution<float> U(0.f, 1.f);
+    auto& env = scene.GetEnvSettings();
+    Camera cam;
+    cam.name = "Cam";
+    cam.ModelView = lookAt(vec3(-9.0, 3.2, 9.0), vec3(0.0, 1.2, 0.0), vec3(0, 1, 0));
+    cam.FieldOfView = 40, cam.Aperture = 0, cam.FocalDistance = 10;
+    env.cameras.push_back(cam);
+    env.HasSky = true, env.HasSun = true, env.SkyIntensity = 1.0f, env.SunIntensity = 20.f, env.SunRotation = 0.35f;
+
+    scene.Materials().push_back({"floor", 0, Material::Lambertian(vec3(0.7f, 0.7f, 0.7f))});
+    scene.Materials().push_back({"wall", 1, Material::Lambertian(vec3(0.6f, 0.55f, 0.5f))});
+    const uint32_t pal = addMaterialPalette(scene, rng, 64);
+
+    Model shell = Model::CreateBox(vec3(-10, -0.2f, -10), vec3(10, 0, 10));
+    Model wallZ = Model::CreateBox(vec3(-9.97f, -0.1f, -0.1f), vec3(9.97f, 4, 0.1f));
+    Model wallX = Model::CreateBox(vec3(-0.1f, -0.13f, -10.23f), vec3(0.1f, 4.05f, 10.23f));
+    shell.Append(wallZ, translate(vec3(0, 0, -10.1f)), 1);
+    shell.Append(wallZ, translate(vec3(0, 0, 10.1f)), 1);
+    shell.Append(wallX, translate(vec3(-10.1f, 0, 0)), 1);
+    shell.Append(wallX, translate(vec3(10.1f, 0, 0)), 1);
+    scene.Models().push_back(shell);
+    addNode(scene, "shell", vec3(0, 0, 0), quat(1, 0, 0, 0), vec3(1, 1, 1), 0, {0, 1});
+
+    uint64_t tris = scene.Models()[0].NumberOfIndices() / 3;
+    uint32_t k = 0;
+    while (tris < targetTriangles) {
+        // bumpy boxes (12 n^2 triangles, own random surface) and tessellated spheres of varying resolution
+        Model m = (k % 3 == 2) ? Model::CreateUVSphere(vec3(0, 0, 0), 0.5f, 40 + (int)(U(rng) * 24.f), 20 + (int)(U(rng) * 12.f))
+                               : Model::CreateGridBox(vec3(-0.5f, -0.5f, -0.5f), vec3(0.5f, 0.5f, 0.5f), 10 + (int)(U(rng) * 8.f), 0.08f, seed * 977u + k);
+        const uint32_t id = (uint32_t)scene.Models().size();
+        tris += m.NumberOfIndices() / 3;
+        scene.Models().push_back(std::move(m));
+        const vec3 t(-9.5f + 19.f * U(rng), 0.3f + 3.4f * U(rng), -9.5f + 19.f * U(rng));
+        const quat r(vec3(6.2831853f * U(rng), 6.2831853f * U(rng), 6.2831853f * U(rng)));
+        const float sc = 0.35f + 0.9f * U(rng);
+        addNode(scene, "obj", t, r, vec3(sc, sc * (0.6f + 0.8f * U(rng)), sc), id, {pal + (uint32_t)(U(rng) * 64.f) % 64});
+        ++k;
+    }
+}
+
 static Model makeBrick(int nx, int nz)
 {
     // LEGO-like brick on the reference's lattice (src/MagicaLego/MagicaLegoGameInstance.cpp:38-45):

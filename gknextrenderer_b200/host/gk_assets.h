@@ -195,6 +195,7 @@ namespace gk::SceneList {
 // scenes defined in SURVEY.md §8(d).
 void CornellBox(Assets::Scene& scene);
 void ProceduralRoom(Assets::Scene& scene, uint32_t targetTriangles = 1000000, uint32_t seed = 1234);
+void ProceduralRoomUnique(Assets::Scene& scene, uint32_t targetTriangles, uint32_t seed = 1234); // every object its own model: no instancing
 void BrickField(Assets::Scene& scene, uint32_t brickCount = 200000, uint32_t seed = 42);
 void BrickFieldStep(Assets::Scene& scene, uint32_t frame, uint32_t seed = 42); // moves 1 % of the bricks
 void InstancedCity(Assets::Scene& scene, uint32_t buildingVariants = 40, uint32_t gridSide = 100, uint32_t seed = 7, int facadeN = 46);

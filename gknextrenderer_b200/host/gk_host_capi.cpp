@@ -28,7 +28,7 @@ extern "C" {
 
 const char* gkh_last_error() { return g_err.c_str(); }
 
-// scene names: "cornell", "room" (p0 = target triangles, p1 = seed), "bricks" (p0 = count, p1 = seed),
+// scene names: "cornell", "room" / "roomu" (instanced / unique geometry; p0 = target triangles, p1 = seed), "bricks" (p0 = count, p1 = seed),
 // "city" (p0 = variants, p1 = grid side, p2 = seed, p3 = facade subdivisions), "empty"
 void* gkh_engine_create(const char* sceneName, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3)
 {
@@ -37,6 +37,7 @@ void* gkh_engine_create(const char* sceneName, uint32_t p0, uint32_t p1, uint32_
         const std::string n = sceneName ? sceneName : "";
         if (n == "cornell") SceneList::CornellBox(e->scene);
         else if (n == "room") SceneList::ProceduralRoom(e->scene, p0 ? p0 : 1000000u, p1 ? p1 : 1234u);
+        else if (n == "roomu") SceneList::ProceduralRoomUnique(e->scene, p0 ? p0 : 1000000u, p1 ? p1 : 1234u);
         else if (n == "bricks") SceneList::BrickField(e->scene, p0 ? p0 : 200000u, p1 ? p1 : 42u);
         else if (n == "city") SceneList::InstancedCity(e->scene, p0 ? p0 : 40u, p1 ? p1 : 100u, p2 ? p2 : 7u, p3 ? (int)p3 : 46);
         else if (n == "empty") {

@@ -102,6 +102,12 @@ typedef struct GkFrameStats {
     uint64_t tailExtensionRays, tailShadowRays; /* part of extensionRays / shadowRays traced by that launch */
     uint32_t maxStack;  /* traversal statistics: deepest stack seen; GK_TRAVERSAL_STACK + 1 means an entry was dropped */
     float msTrace;      /* extend + shadow kernels of all waves as one span per wave (the two run concurrently) */
+    /* traversal statistics of the scheduled kernel (gk_set_traversal_stats): steps the warps ran per class
+     * (0 node visit, 1 triangle test, 2 instance entry) and the lanes that took part; lanes / (32 * iters) is the
+     * SIMD occupancy of that step */
+    uint64_t schedIters[3], schedLanes[3];
+    uint64_t schedRefills, schedRefillLanes; /* queue refills per warp and rays fetched by them */
+    uint64_t schedPopIters, schedPopLanes;   /* iterations in which some lane popped its stack, lanes popping */
 } GkFrameStats;
 
 typedef struct GkBvhInfo {
@@ -231,6 +237,11 @@ void gk_host_free(void* p);
 GkStatus gk_synchronize(GkContext* ctx);
 GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out);
 GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out);
+/* Tuning hooks (the defaults are the measured optima; DESIGN.md lists the sweeps).  Unknown names return
+ * GK_ERR_INVALID_ARGUMENT.  Names: "trace_variant" (0 while-while lane kernel + cooperative kernel, 1 persistent
+ * vote-scheduled kernel), "sched_refill_min", "sched_bias_node", "sched_min_rays", "coop_threshold", "tail_threshold",
+ * "tail_fraction", "concurrent_shadow", "wave_lookahead". */
+GkStatus gk_set_option(GkContext* ctx, const char* name, double value);
 /* Enables node-visit / triangle-test counters in the traversal kernels (slower). */
 GkStatus gk_set_traversal_stats(GkContext* ctx, int enabled);
 /* CUDA stream used by the context (cudaStream_t), for callers that order their own work. */
