@@ -192,6 +192,12 @@ __device__ __forceinline__ bool childTest(const NodeFrame& F, const PlaneSel& S,
     return tn <= tf * kBoxTolerance;
 }
 
+// NOTE (round 2): traverseCoop / traverseLane are the round-1 kernels, kept byte for byte as trace variant 0 (the A/B
+// baseline of the scheduled kernel in gk_trace_sched.cuh, which is the production path and reports stack overflow
+// through SceneView::overflowFlag).  Adding an overflow store to traverseLane made ptxas address the local-memory stack
+// through a uniform register that the code after the loop reuses; lanes leaving the any-hit loop early then corrupted
+// the stack base of the lanes still inside (compute-sanitizer: invalid __local__ read at the tuv pointer's low word +
+// 8*sp).  These two functions only report a dropped entry through the traversal statistics (maxStack).
 // ---- cooperative mapping: eight lanes per ray ---------------------------------------------------
 // Every lane of the group passes the same ray and receives the same result.  `stackRow` points at
 // the group's row of kStackSize uint2 entries in shared memory.  Dn is the NORMALISED world
@@ -230,12 +236,11 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
                 const uint32_t key = __reduce_min_sync(gmask, hitBox ? ((__float_as_uint(tn) & ~7u) | sub) : 0xffffffffu);
                 const unsigned near = key & 7u;
                 const unsigned others = m & ~(1u << near);
-                const int room = kStackSize - 1 - sp; // the last slot is reserved for the return-to-TLAS marker
+                const int room = kStackSize - sp;
                 if (hitBox && sub != near) {
                     const int rank = __popc(others & ((1u << sub) - 1u));
                     if (rank < room) stackRow[sp + rank] = make_uint2(ref, __float_as_uint(tn));
                 }
-                if (__popc(others) > room && sub == 0) *S.overflowFlag = 1u; // an entry was dropped: a hit may be missed
                 if (kStats && sub == 0) {
                     if (__popc(others) > room) stats->maxStack = kStackSize + 1;
                     else if ((unsigned long long)(sp + __popc(others)) > stats->maxStack) stats->maxStack = sp + __popc(others);
@@ -252,8 +257,8 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
             const uint4 tail = __ldg(reinterpret_cast<const uint4*>(ip + 4));
             const float T[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
             if (kStats && sub == 0) stats->instanceEntries++;
-            if (sub == 0) stackRow[sp] = make_uint2(kSentinel, 0u); // sp <= kStackSize - 1: children never take the last slot
-            ++sp;
+            if (sub == 0 && sp < kStackSize) stackRow[sp] = make_uint2(kSentinel, 0u);
+            sp = min(sp + 1, kStackSize);
             o = xformPoint(O, T);
             d = xformVector(Dn, T);
             rd = boxRcp3(d);
@@ -373,13 +378,8 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
                         uint32_t pr = ref;
                         float pt = tn;
                         if (tn < bestT) { pr = bestRef, pt = bestT, bestRef = ref, bestT = tn; }
-                        if (pr != kInvalid) {
-                            if (sp < kStackSize - 1) stk.e[sp++] = make_uint2(pr, __float_as_uint(pt)); // last slot: reserved for the return-to-TLAS marker
-                            else {
-                                *S.overflowFlag = 1u; // an entry was dropped: a hit may be missed; the host reports it
-                                if (kStats) stats->maxStack = kStackSize + 1;
-                            }
-                        }
+                        if (pr != kInvalid && sp < kStackSize) stk.e[sp++] = make_uint2(pr, __float_as_uint(pt));
+                        else if (kStats && pr != kInvalid) stats->maxStack = kStackSize + 1; // an entry was dropped
                     }
                 }
             }
@@ -396,7 +396,7 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
             const uint4 tail = __ldg(reinterpret_cast<const uint4*>(ip + 4));
             const float T[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
             if (kStats) stats->instanceEntries++;
-            stk.e[sp++] = make_uint2(kSentinel, 0u); // always fits: children never take the last slot
+            if (sp < kStackSize) stk.e[sp++] = make_uint2(kSentinel, 0u);
             o = xformPoint(O, T);
             d = xformVector(Dn, T);
             rd = boxRcp3(d);

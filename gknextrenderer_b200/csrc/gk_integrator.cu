@@ -955,7 +955,8 @@ GkStatus traceFrame(Context& c)
     uint32_t countE = n, countS = 0;
     bool tailRan = false;
     // the tail launch pays off once the waves are short: a quarter of the paths (swept on 1, 2 and 4 GPUs), capped per SM
-    const uint32_t tailLimit = std::min(c.tailThreshold, (uint32_t)(c.tailFraction * (float)n));
+    // (the scheduled kernel balances short waves by itself and is the only kernel that reports stack overflow: no tail launch with it)
+    const uint32_t tailLimit = c.traceVariant == 1 ? 0u : std::min(c.tailThreshold, (uint32_t)(c.tailFraction * (float)n));
     fs.tailPaths = 0;
     fs.tailExtensionRays = fs.tailShadowRays = 0;
     fs.primaryRays = (uint64_t)c.ownedRows * c.width;
