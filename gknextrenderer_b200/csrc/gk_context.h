@@ -208,6 +208,8 @@ struct Context {
     int traceVariant = 1;            // 0: while-while lane kernel / cooperative kernel, 1: persistent vote-scheduled kernel
     uint32_t schedRefillMin = 8;     // refill a warp's idle lanes once this many rays have finished
     uint32_t schedBiasN = 0;         // vote bias towards the node step (lanes)
+    uint32_t schedKeepN = 12;        // a node phase goes on while this many lanes hold a node (33: one step per vote)
+    uint32_t schedKeepT = 10;        // ditto for the triangle phase
     uint32_t schedMinRays = 0;       // waves smaller than this keep the variant-0 kernels
     int schedBlocksPerSm = 0, smCount = 0;
     static constexpr uint32_t kCursorCount = 1024;
@@ -215,7 +217,11 @@ struct Context {
     uint32_t cursorNext = 0;
     struct SchedStats* dSchedStats = nullptr;
     uint32_t* dOverflow = nullptr;   // set by a traversal that had to drop a stack entry
-    uint32_t waveLookahead = 4;      // waves the host may run ahead of the device in the wave loop
+    uint32_t waveLookahead = 2;      // waves the host runs ahead of the device's published queue sizes (streamed wave loop)
+    static constexpr uint32_t kWaveLimit = 4096;
+    volatile uint32_t* hWave = nullptr; // mapped pinned memory: 4 words per wave {next extend count, next shadow count, frame tag, -}
+    uint32_t* dWave = nullptr;          // the same memory as the device sees it
+    uint32_t frameTag = 0;
     DevBuf<float4> dCapture;
     uint32_t capturedCount = 0;
     uint64_t frameIndex = 0;

@@ -22,6 +22,8 @@
 #include "gk_context.h"
 #include "gk_shading.cuh"
 #include "gk_trace_sched.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace gk {
 
@@ -160,9 +162,10 @@ template <bool kAny> struct ArrayIO { // RayIO over interleaved {O|tmin, D|tmax}
 
 // One kernel body for extend / shadow / intersect.
 template <bool kAnyHit, bool kCoop, bool kStats, class RayIO>
-__global__ void __launch_bounds__(256, kCoop ? 2 : 4) k_trace(SceneView V, RayIO io, uint32_t count, TraversalStats* stats)
+__global__ void __launch_bounds__(256, kCoop ? 2 : 4) k_trace(SceneView V, RayIO io, uint32_t count, TraversalStats* stats, const uint32_t* __restrict__ countPtr)
 {
     __shared__ uint2 stack[kCoop ? kRaysPerBlock * kStackStride : 1];
+    if (countPtr) count = *countPtr; // device-driven wave loop: `count` only sized the grid
     TraversalStats local{0, 0};
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = kCoop ? (gt >> 3) : gt;
@@ -192,12 +195,12 @@ __global__ void __launch_bounds__(256, kCoop ? 2 : 4) k_trace(SceneView V, RayIO
 // The scheduled (persistent, vote-driven) traversal kernel: gk_trace_sched.cuh.  `countPtr` (device) overrides
 // `countImm` so that a wave can be launched before the host knows its size.
 template <bool kAnyHit, bool kStats, class RayIO>
-__global__ void __launch_bounds__(kSchedBlock, 4) k_trace_sched(SceneView V, RayIO io, const uint32_t* __restrict__ countPtr, uint32_t countImm, uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(kSchedBlock, 6) k_trace_sched(SceneView V, RayIO io, const uint32_t* __restrict__ countPtr, uint32_t countImm, uint32_t* __restrict__ cursor,
                                                               SchedParams prm, TraversalStats* stats, SchedStats* sched)
 {
-    __shared__ uint32_t sStack[2 * kSmemStack * kSchedBlock];
+    __shared__ uint32_t sMem[kSchedSmemWords];
     const uint32_t count = countPtr ? *countPtr : countImm;
-    traverseScheduled<kAnyHit, kStats, RayIO>(V, io, count, cursor, prm, sStack, stats, sched);
+    traverseScheduled<kAnyHit, kStats, RayIO>(V, io, count, cursor, prm, sMem, stats, sched);
 }
 
 // -------------------------------------------------------------------------------- shade
@@ -635,6 +638,38 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_shade(const GkUniformBuffer
     appendRay(e, path, outE, outS);
 }
 
+// Device-driven form of the same kernel: the queue sizes are read from device memory and the blocks stride over the
+// queue, so a wave can be enqueued before the host knows how many rays the previous wave produced.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_shade_stream(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, ShadeScene SS, PathState S, PlaneView PL, RayQueue inE,
+                                                      RayQueue inS, RayQueue outE, RayQueue outS)
+{
+    const uint32_t countE = *inE.count, countS = *inS.count, total = countE + countS;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) { // block-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        Emit e;
+        e.kind = 0;
+        uint32_t path = 0;
+        if (i < total) {
+            const bool fromExtend = i < countE;
+            const uint32_t slot = fromExtend ? i : i - countE;
+            path = fromExtend ? inE.path[slot] : inS.path[slot];
+            shadePath(*ubo, P, SS, S, PL, path, QueueSrc{inE, inS, slot}, e);
+        }
+        appendRay(e, path, outE, outS);
+    }
+}
+
+// End of a wave: publishes the sizes of the next wave's queues to the host (mapped pinned memory; the tag goes last).
+// The host polls these slots a few waves behind the device instead of synchronising the stream after every wave.
+__global__ void k_wave_end(const uint32_t* __restrict__ nextE, const uint32_t* __restrict__ nextS, volatile uint32_t* hostSlot, uint32_t tag)
+{
+    hostSlot[0] = *nextE;
+    hostSlot[1] = *nextS;
+    __threadfence_system();
+    hostSlot[2] = tag;
+}
+
 // Tail of the frame: when few paths are still alive, one launch walks every one of them to its end
 // (trace -> shade -> trace ...), one path per lane, instead of paying three launches and a queue
 // count read-back per wave.  counters[0] / [1] receive the extension / shadow rays traced here.
@@ -696,10 +731,18 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams P, PathState S, 
 
 // -------------------------------------------------------------------------------- utilities
 template <bool kAnyHit, bool kCoop, class RayIO>
-static void launchMapped(cudaStream_t st, unsigned grid, unsigned block, const SceneView& V, const RayIO& io, uint32_t count, TraversalStats* ts)
+static void launchMapped(cudaStream_t st, unsigned grid, unsigned block, const SceneView& V, const RayIO& io, uint32_t count, TraversalStats* ts, const uint32_t* countPtr = nullptr)
 {
-    if (ts) k_trace<kAnyHit, kCoop, true, RayIO><<<grid, block, 0, st>>>(V, io, count, ts);
-    else k_trace<kAnyHit, kCoop, false, RayIO><<<grid, block, 0, st>>>(V, io, count, ts);
+    if (ts) k_trace<kAnyHit, kCoop, true, RayIO><<<grid, block, 0, st>>>(V, io, count, ts, countPtr);
+    else k_trace<kAnyHit, kCoop, false, RayIO><<<grid, block, 0, st>>>(V, io, count, ts, countPtr);
+}
+
+// Small waves of the streamed loop: the eight-lanes-per-ray kernel (lowest latency per ray), sized by an upper bound.
+template <bool kAnyHit, class RayIO>
+static void launchCoopBounded(Context& c, const SceneView& V, const RayIO& io, uint32_t bound, cudaStream_t stream, const uint32_t* countPtr)
+{
+    const unsigned grid = std::max(1u, (bound + kRaysPerBlock - 1) / kRaysPerBlock);
+    launchMapped<kAnyHit, true>(stream, grid, 256, V, io, bound, c.travStats ? c.dTravStats : nullptr, countPtr);
 }
 
 // Next zeroed fetch cursor of the frame (the block of cursors is cleared once per frame / per intersect call).
@@ -715,8 +758,9 @@ static uint32_t* nextCursor(Context& c, cudaStream_t)
     return c.dCursors + c.cursorNext++;
 }
 
+// `count` sizes the grid (an upper bound is enough when `countPtr` supplies the exact number on the device).
 template <bool kAnyHit, class RayIO>
-static void launchSched(Context& c, const SceneView& V, const RayIO& io, uint32_t count, cudaStream_t stream)
+static void launchSched(Context& c, const SceneView& V, const RayIO& io, uint32_t count, cudaStream_t stream, const uint32_t* countPtr = nullptr)
 {
     if (c.schedBlocksPerSm == 0) {
         int nb = 0, sms = 0;
@@ -726,10 +770,10 @@ static void launchSched(Context& c, const SceneView& V, const RayIO& io, uint32_
     }
     const unsigned resident = (unsigned)(c.schedBlocksPerSm * c.smCount);
     const unsigned grid = std::max(1u, std::min(resident, (count + kSchedBlock - 1) / kSchedBlock));
-    const SchedParams prm{std::min(32u, std::max(1u, c.schedRefillMin)), c.schedBiasN};
+    const SchedParams prm{std::min(32u, std::max(1u, c.schedRefillMin)), c.schedBiasN, std::min(33u, std::max(1u, c.schedKeepN)), std::min(33u, std::max(1u, c.schedKeepT))};
     uint32_t* cursor = nextCursor(c, stream);
-    if (c.travStats) k_trace_sched<kAnyHit, true, RayIO><<<grid, kSchedBlock, 0, stream>>>(V, io, nullptr, count, cursor, prm, c.dTravStats, c.dSchedStats);
-    else k_trace_sched<kAnyHit, false, RayIO><<<grid, kSchedBlock, 0, stream>>>(V, io, nullptr, count, cursor, prm, nullptr, nullptr);
+    if (c.travStats) k_trace_sched<kAnyHit, true, RayIO><<<grid, kSchedBlock, 0, stream>>>(V, io, countPtr, count, cursor, prm, c.dTravStats, c.dSchedStats);
+    else k_trace_sched<kAnyHit, false, RayIO><<<grid, kSchedBlock, 0, stream>>>(V, io, countPtr, count, cursor, prm, nullptr, nullptr);
 }
 
 template <bool kAnyHit, class RayIO>
@@ -796,6 +840,8 @@ void freeFrameResources(Context& c)
     c.dSchedStats = nullptr;
     if (c.dOverflow) cudaFree(c.dOverflow);
     c.dOverflow = nullptr;
+    if (c.hWave) cudaFreeHost((void*)c.hWave);
+    c.hWave = nullptr, c.dWave = nullptr;
 }
 
 static size_t planePixelBytes(int plane)
@@ -900,6 +946,213 @@ static cudaEvent_t poolEvent(Context& c, size_t i)
     return c.evPool[i];
 }
 
+// Waits until the device has published wave slot `w` of this frame (k_wave_end); polls pinned memory, no stream sync.
+static GkStatus waitWaveSlot(Context& c, uint32_t w, uint32_t tag, uint32_t& countE, uint32_t& countS)
+{
+    volatile uint32_t* slot = c.hWave + 4 * (size_t)w;
+    for (uint64_t spin = 0; slot[2] != tag; ++spin) {
+        __builtin_ia32_pause();
+        if ((spin & 0xfffffu) == 0xfffffu) { // every ~million polls: has the stream died?
+            const cudaError_t e = cudaStreamQuery(c.stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) {
+                setLastError(std::string("gk_trace_frame: ") + cudaGetErrorString(e));
+                return GK_ERR_CUDA;
+            }
+        }
+    }
+    countE = slot[0], countS = slot[1];
+    return GK_OK;
+}
+
+// The wave loop of the scheduled kernels: every kernel takes its queue sizes from device memory, so the host enqueues
+// wave w without knowing how many rays wave w-1 produced.  It learns the sizes `waveLookahead` waves late from slots the
+// device writes into mapped pinned memory (k_wave_end) and stops enqueuing once a wave was empty; at most `waveLookahead`
+// empty waves (a few microseconds of launches each) are enqueued.  No stream synchronisation inside the frame.
+static GkStatus traceFrameStreamed(Context& c)
+{
+    cudaStream_t st = c.stream;
+    const uint32_t n = c.pathCount;
+    FrameParams P{c.width, c.height, c.traceTileIndex, c.traceTileCount, c.tileRows, n};
+    const SceneView V = c.view();
+    const ShadeScene SS = shadeSceneOf(c);
+    const PlaneView PL = planeViewOf(c);
+    GkFrameStats& fs = c.stats;
+    fs.primaryRays = fs.extensionRays = fs.shadowRays = 0;
+    fs.waves = fs.launches = 0;
+    fs.msGenerate = fs.msExtend = fs.msShade = fs.msShadow = fs.msAccumulate = fs.msTail = fs.msTrace = 0;
+    fs.tailPaths = 0, fs.tailExtensionRays = fs.tailShadowRays = 0;
+    size_t ev = 0;
+    struct Span { size_t a, b; int kind; };
+    std::vector<Span> spans;
+    auto mark = [&]() { cudaEvent_t e = poolEvent(c, ev); cudaEventRecord(e, st); return ev++; };
+    auto markOn = [&](cudaStream_t s2) { cudaEvent_t e = poolEvent(c, ev); cudaEventRecord(e, s2); return ev++; };
+    if (c.concurrentShadow && !c.stream2) {
+        GK_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+        GK_CUDA(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
+        GK_CUDA(cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming));
+    }
+    if (!c.hWave) {
+        GK_CUDA(cudaHostAlloc((void**)&c.hWave, sizeof(uint32_t) * 4 * Context::kWaveLimit, cudaHostAllocMapped));
+        memset((void*)c.hWave, 0, sizeof(uint32_t) * 4 * Context::kWaveLimit);
+        GK_CUDA(cudaHostGetDevicePointer((void**)&c.dWave, (void*)c.hWave, 0));
+    }
+    const uint32_t tag = ++c.frameTag ? c.frameTag : ++c.frameTag; // never 0
+    GK_CUDA(cudaMemcpyAsync(c.dUbo, &c.ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, st));
+    if (c.travStats) {
+        GK_CUDA(cudaMemsetAsync(c.dTravStats, 0, sizeof(TraversalStats), st));
+        GK_CUDA(cudaMemsetAsync(c.dSchedStats, 0, sizeof(SchedStats), st));
+    }
+    if (c.cursorNext) { // queue cursors of the previous frame's launches
+        GK_CUDA(cudaMemsetAsync(c.dCursors, 0, sizeof(uint32_t) * c.cursorNext, st));
+        c.cursorNext = 0;
+    }
+    const size_t evStart = mark();
+    k_generate<<<gridFor(n), 256, 0, st>>>(c.dUbo, P, c.paths, c.extendQ[0]);
+    fs.launches++;
+    GK_CUDA(cudaMemsetAsync(c.shadowQ[0].count, 0, sizeof(uint32_t), st));
+    const size_t evGen = mark();
+    spans.push_back({evStart, evGen, 0});
+    fs.primaryRays = (uint64_t)c.ownedRows * c.width;
+    c.capturedCount = 0;
+    // capture / statistics frames keep the host in lock step (it needs the exact size of the wave it is about to enqueue)
+    const uint32_t look = (c.captureWave >= 0) ? 0u : c.waveLookahead;
+    int shadeBlocksPerSm = c.shadeMinBlocks >= 4 ? 4 : c.shadeMinBlocks >= 3 ? 3 : 2;
+    if (c.smCount == 0) cudaDeviceGetAttribute(&c.smCount, cudaDevAttrMultiProcessorCount, c.device);
+    uint32_t bound = n;      // upper bound of the rays of the wave being enqueued (paths alive never increase)
+    uint32_t enqueued = 0;   // waves enqueued so far
+    uint32_t known = 0;      // slots read so far: slot w holds the queue sizes of wave w + 1
+    bool drained = false;
+    auto consume = [&](uint32_t upTo) -> GkStatus { // reads slots [known, upTo)
+        for (; known < upTo; ++known) {
+            uint32_t e = 0, s2 = 0;
+            const GkStatus r = waitWaveSlot(c, known, tag, e, s2);
+            if (r != GK_OK) return r;
+            fs.extensionRays += e, fs.shadowRays += s2;
+            if (e + s2) fs.waves = known + 2;
+            else drained = true;
+            bound = e + s2;
+        }
+        return GK_OK;
+    };
+    fs.waves = 1;
+    for (uint32_t wave = 0; wave < Context::kWaveLimit; ++wave) {
+        if (wave > look) {
+            const GkStatus r = consume(wave - look);
+            if (r != GK_OK) return r;
+            if (drained) break;
+        }
+        const int cur = (int)(wave & 1u), nxt = cur ^ 1;
+        const uint32_t sizeE = wave == 0 ? n : bound, sizeS = wave == 0 ? 0u : bound;
+        const size_t a = mark();
+        if ((int)wave == c.captureWave && look == 0) {
+            const uint32_t countE = wave == 0 ? n : c.hWave[4 * (size_t)(wave - 1)];
+            if (countE) {
+                GK_CUDA(c.dCapture.reserve(2 * (size_t)countE));
+                GK_CUDA(cudaMemcpy2DAsync(c.dCapture.p, 32, c.extendQ[cur].o_tmin, 16, 16, countE, cudaMemcpyDeviceToDevice, st));
+                GK_CUDA(cudaMemcpy2DAsync(c.dCapture.p + 1, 32, c.extendQ[cur].d_tmax, 16, 16, countE, cudaMemcpyDeviceToDevice, st));
+            }
+            c.capturedCount = countE;
+        }
+        // extend and shadow rays of a wave are independent: two streams, so that one kernel's blocks fill the SMs the other's tail leaves idle
+        const bool fork = sizeS && c.concurrentShadow;
+        // waves below the threshold: the eight-lanes-per-ray kernel (a lone ray finishes ~4x sooner than on one lane); `bound` is
+        // the size of an earlier wave, so a wave is only classed small when it certainly is
+        const bool small = wave > 0 && bound < c.coopThreshold;
+        size_t b, d, s0 = 0, s1 = 0;
+        if (fork) {
+            GK_CUDA(cudaEventRecord(c.evFork, st));
+            GK_CUDA(cudaStreamWaitEvent(c.stream2, c.evFork, 0));
+            s0 = markOn(c.stream2);
+            if (small) launchCoopBounded<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, c.stream2, c.shadowQ[cur].count);
+            else launchSched<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, c.stream2, c.shadowQ[cur].count);
+            s1 = markOn(c.stream2);
+            GK_CUDA(cudaEventRecord(c.evJoin, c.stream2));
+            if (small) launchCoopBounded<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, st, c.extendQ[cur].count);
+            else launchSched<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, st, c.extendQ[cur].count);
+            b = mark();
+            GK_CUDA(cudaStreamWaitEvent(st, c.evJoin, 0));
+            d = mark();
+            fs.launches += 2;
+        } else {
+            if (small) launchCoopBounded<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, st, c.extendQ[cur].count);
+            else launchSched<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, st, c.extendQ[cur].count);
+            fs.launches++;
+            b = mark();
+            if (sizeS) {
+                if (small) launchCoopBounded<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, st, c.shadowQ[cur].count);
+                else launchSched<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, st, c.shadowQ[cur].count);
+                fs.launches++;
+            }
+            d = mark();
+        }
+        GK_CUDA(cudaMemsetAsync(c.extendQ[nxt].count, 0, sizeof(uint32_t), st));
+        GK_CUDA(cudaMemsetAsync(c.shadowQ[nxt].count, 0, sizeof(uint32_t), st));
+        const unsigned shadeGrid = std::max(1u, std::min((unsigned)(c.smCount * shadeBlocksPerSm * 2), (unsigned)gridFor((size_t)sizeE + sizeS)));
+        if (shadeBlocksPerSm == 4) k_shade_stream<4><<<shadeGrid, 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
+        else if (shadeBlocksPerSm == 3) k_shade_stream<3><<<shadeGrid, 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
+        else k_shade_stream<2><<<shadeGrid, 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
+        const size_t f = mark();
+        k_wave_end<<<1, 1, 0, st>>>(c.extendQ[nxt].count, c.shadowQ[nxt].count, c.dWave + 4 * (size_t)wave, tag);
+        fs.launches += 2;
+        spans.push_back({a, b, 1}), spans.push_back({d, f, 3}), spans.push_back({a, d, 6});
+        if (fork) spans.push_back({s0, s1, 2});
+        else spans.push_back({b, d, 2});
+        enqueued = wave + 1;
+    }
+    {
+        const GkStatus r = consume(enqueued);
+        if (r != GK_OK) return r;
+    }
+    if (!drained) {
+        GK_CUDA(cudaStreamSynchronize(st));
+        setLastError("gk_trace_frame: paths were still alive after the wave limit (" + std::to_string(Context::kWaveLimit) + "); lower NumberOfSamples / bounces");
+        return GK_ERR_UNSUPPORTED;
+    }
+    const size_t g = mark();
+    k_accumulate<<<gridFor(n), 256, 0, st>>>(P, c.paths, PL);
+    fs.launches++;
+    const size_t hEnd = mark();
+    spans.push_back({g, hEnd, 4});
+    GK_CUDA(cudaGetLastError());
+    GK_CUDA(cudaMemcpyAsync(c.hCounts + 12, c.dOverflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st)); // traversal stack overflow flag
+    GK_CUDA(cudaStreamSynchronize(st));
+    for (const Span& sp : spans) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.evPool[sp.a], c.evPool[sp.b]);
+        if (sp.kind == 0) fs.msGenerate += ms;
+        else if (sp.kind == 1) fs.msExtend += ms;
+        else if (sp.kind == 2) fs.msShadow += ms;
+        else if (sp.kind == 3) fs.msShade += ms;
+        else if (sp.kind == 6) fs.msTrace += ms;
+        else fs.msAccumulate += ms;
+    }
+    cudaEventElapsedTime(&fs.msTotal, c.evPool[evStart], c.evPool[hEnd]);
+    if (getenv("GK_WAVE_LOG")) { // per-wave device times (diagnostics): trace span, shade span, queue sizes
+        size_t k = 1;
+        for (uint32_t w = 0; w < enqueued && k + 2 < spans.size(); ++w, k += 4) {
+            float tr = 0, sh = 0;
+            cudaEventElapsedTime(&tr, c.evPool[spans[k + 2].a], c.evPool[spans[k + 2].b]);
+            cudaEventElapsedTime(&sh, c.evPool[spans[k + 1].a], c.evPool[spans[k + 1].b]);
+            const uint32_t e = w == 0 ? n : c.hWave[4 * (size_t)(w - 1)], s2 = w == 0 ? 0u : c.hWave[4 * (size_t)(w - 1) + 1];
+            fprintf(stderr, "[gk wave %2u] extend %8u shadow %8u rays  trace %.3f ms  shade %.3f ms\n", w, e, s2, tr, sh);
+        }
+    }
+    if (c.travStats) {
+        TraversalStats h;
+        GK_CUDA(cudaMemcpy(&h, c.dTravStats, sizeof(h), cudaMemcpyDeviceToHost));
+        fs.nodeVisits = h.nodeVisits, fs.triTests = h.triTests, fs.tlasVisits = h.tlasVisits, fs.instanceEntries = h.instanceEntries, fs.maxStack = (uint32_t)h.maxStack;
+        SchedStats ss;
+        GK_CUDA(cudaMemcpy(&ss, c.dSchedStats, sizeof(ss), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 3; ++k) fs.schedIters[k] = ss.iters[k], fs.schedLanes[k] = ss.lanes[k];
+        fs.schedRefills = ss.refills, fs.schedRefillLanes = ss.refillLanes, fs.schedPopIters = ss.popIters, fs.schedPopLanes = ss.popLanes;
+    }
+    if (c.hCounts[12]) {
+        c.hCounts[12] = 0;
+        return checkTraversalOverflow(c);
+    }
+    return GK_OK;
+}
+
 GkStatus traceFrame(Context& c)
 {
     if (!c.haveScene || !c.haveInstances || !c.haveUbo) {
@@ -916,6 +1169,7 @@ GkStatus traceFrame(Context& c)
         waitAsyncCopyBeforeWriting(c, bufs, (int)(sizeof(written) / sizeof(written[0])));
     }
     c.tracedSinceFilter = true;
+    if (c.traceVariant == 1) return traceFrameStreamed(c);
     const uint32_t n = c.pathCount;
     FrameParams P{c.width, c.height, c.traceTileIndex, c.traceTileCount, c.tileRows, n};
     const SceneView V = c.view();

@@ -107,7 +107,7 @@ typedef struct GkFrameStats {
      * SIMD occupancy of that step */
     uint64_t schedIters[3], schedLanes[3];
     uint64_t schedRefills, schedRefillLanes; /* queue refills per warp and rays fetched by them */
-    uint64_t schedPopIters, schedPopLanes;   /* iterations in which some lane popped its stack, lanes popping */
+    uint64_t schedPopIters, schedPopLanes;   /* votes taken by the warps, lanes alive at those votes */
 } GkFrameStats;
 
 typedef struct GkBvhInfo {
@@ -239,7 +239,7 @@ GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out);
 GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out);
 /* Tuning hooks (the defaults are the measured optima; DESIGN.md lists the sweeps).  Unknown names return
  * GK_ERR_INVALID_ARGUMENT.  Names: "trace_variant" (0 while-while lane kernel + cooperative kernel, 1 persistent
- * vote-scheduled kernel), "sched_refill_min", "sched_bias_node", "sched_min_rays", "coop_threshold", "tail_threshold",
+ * vote-scheduled kernel), "sched_refill_min", "sched_bias_node", "sched_keep_node", "sched_keep_tri", "sched_min_rays", "coop_threshold", "tail_threshold",
  * "tail_fraction", "concurrent_shadow", "wave_lookahead". */
 GkStatus gk_set_option(GkContext* ctx, const char* name, double value);
 /* Enables node-visit / triangle-test counters in the traversal kernels (slower). */

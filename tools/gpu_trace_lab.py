@@ -21,16 +21,21 @@ import torch  # noqa: E402
 import gknextrenderer_b200 as gk  # noqa: E402
 from bench import WORKLOADS  # noqa: E402
 
+def _sched(refill=8, bias=0, keep_n=12, keep_t=10):
+    return dict(trace_variant=1, sched_refill_min=refill, sched_bias_node=bias, sched_keep_node=keep_n, sched_keep_tri=keep_t)
+
+
 CONFIGS = {
     "legacy": dict(trace_variant=0),
-    "sched_r8": dict(trace_variant=1, sched_refill_min=8, sched_bias_node=0),
-    "sched_r1": dict(trace_variant=1, sched_refill_min=1, sched_bias_node=0),
-    "sched_r4": dict(trace_variant=1, sched_refill_min=4, sched_bias_node=0),
-    "sched_r12": dict(trace_variant=1, sched_refill_min=12, sched_bias_node=0),
-    "sched_r16": dict(trace_variant=1, sched_refill_min=16, sched_bias_node=0),
-    "sched_r32": dict(trace_variant=1, sched_refill_min=32, sched_bias_node=0),
-    "sched_r8_b4": dict(trace_variant=1, sched_refill_min=8, sched_bias_node=4),
-    "sched_r8_b8": dict(trace_variant=1, sched_refill_min=8, sched_bias_node=8),
+    "sched": _sched(),
+    "sched_step": _sched(keep_n=33, keep_t=33),  # one step per vote
+    "sched_kn8": _sched(keep_n=8), "sched_kn16": _sched(keep_n=16), "sched_kn20": _sched(keep_n=20), "sched_kn24": _sched(keep_n=24),
+    "sched_kt4": _sched(keep_t=4), "sched_kt16": _sched(keep_t=16),
+    "sched_r4": _sched(refill=4), "sched_r12": _sched(refill=12), "sched_r16": _sched(refill=16),
+    "sched_b4": _sched(bias=4),
+    "sched_kt4_r4": dict(_sched(refill=4, keep_t=4)),
+    "sched_look0": dict(_sched(keep_t=4), wave_lookahead=0), "sched_look1": dict(_sched(keep_t=4), wave_lookahead=1),
+    "sched_look3": dict(_sched(keep_t=4), wave_lookahead=3), "sched_look2": dict(_sched(keep_t=4), wave_lookahead=2),
 }
 
 
@@ -125,7 +130,7 @@ def main():
                 it, ln = list(st.schedIters), list(st.schedLanes)
                 rec["sched"] = {"lanes_per_step": [round(ln[k] / max(1, it[k]), 2) for k in range(3)], "steps": it,
                                 "rays_per_refill": round(st.schedRefillLanes / max(1, st.schedRefills), 2),
-                                "pop_lanes": round(st.schedPopLanes / max(1, st.schedPopIters), 2), "pop_iters": int(st.schedPopIters)}
+                                "alive_at_vote": round(st.schedPopLanes / max(1, st.schedPopIters), 2), "votes": int(st.schedPopIters)}
             line = json.dumps(rec)
             print(line, flush=True)
             if out:
