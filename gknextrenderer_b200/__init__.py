@@ -206,6 +206,12 @@ class Renderer:
         """Tuning hook (gk_set_option): e.g. trace_variant, sched_refill_min, coop_threshold."""
         self._check(self.lib.gk_set_option(self.h, name.encode(), float(value)))
 
+    def measure_read_bandwidth(self, nbytes: int, reps: int = 8) -> float:
+        """GB/s of the library's streaming-read probe over a scratch buffer of nbytes (L2-resident when small)."""
+        out = C.c_float()
+        self._check(self.lib.gk_measure_read_bandwidth(self.h, nbytes, reps, C.byref(out)))
+        return float(out.value)
+
     def set_traversal_stats(self, on: bool):
         self._check(self.lib.gk_set_traversal_stats(self.h, 1 if on else 0))
 

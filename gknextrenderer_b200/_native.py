@@ -171,6 +171,7 @@ CUDA_API = {
     "gk_get_stats": (C.c_int, [_P, C.POINTER(GkFrameStats)]),
     "gk_get_bvh_info": (C.c_int, [_P, C.POINTER(GkBvhInfo)]),
     "gk_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
+    "gk_measure_read_bandwidth": (C.c_int, [_P, C.c_size_t, C.c_int, C.POINTER(C.c_float)]),
     "gk_set_traversal_stats": (C.c_int, [_P, C.c_int]),
     "gk_stream": (_P, [_P]),
     "gk_set_ray_capture": (C.c_int, [_P, C.c_int]),

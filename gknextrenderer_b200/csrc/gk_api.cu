@@ -47,6 +47,19 @@ __global__ void k_raycast_results(const float* __restrict__ originDir, const flo
     out[i] = R;
 }
 
+// Read-bandwidth probe: every thread streams 128-bit loads (L1 bypassed) over the buffer `reps` times.
+__global__ void __launch_bounds__(256) k_stream_read(const uint4* __restrict__ buf, size_t n16, int reps, uint4* sink)
+{
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < reps; ++r)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            const uint4 v = __ldcg(buf + i);
+            acc.x ^= v.x, acc.y ^= v.y, acc.z ^= v.z, acc.w ^= v.w;
+        }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) *sink = acc; // keeps the loads alive
+}
+
 static GkStatus selectDevice(Context& c)
 {
     GK_CUDA(cudaSetDevice(c.device));
@@ -153,6 +166,7 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
     if (const char* e = getenv("GK_TAIL_THRESHOLD")) c.tailThreshold = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("GK_COOP_THRESHOLD")) c.coopThreshold = (uint32_t)strtoul(e, nullptr, 10); // tuning / test hook
     if (const char* e = getenv("GK_TRACE_VARIANT")) c.traceVariant = atoi(e);
+    if (c.traceVariant != 1 && !getenv("GK_COOP_THRESHOLD")) c.coopThreshold = 65536u;
     if (const char* e = getenv("GK_SCHED_REFILL_MIN")) c.schedRefillMin = (uint32_t)std::min(32, std::max(1, atoi(e)));
     if (const char* e = getenv("GK_SCHED_BIAS_NODE")) c.schedBiasN = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("GK_SCHED_MIN_RAYS")) c.schedMinRays = (uint32_t)strtoul(e, nullptr, 10);
@@ -161,8 +175,16 @@ GkStatus gk_create(const GkConfig* cfg, GkContext** out)
         setLastError("gk_create: tileIndex >= tileCount");
         return GK_ERR_INVALID_ARGUMENT;
     }
-    GK_CUDA(cudaSetDevice(dev));
-    GK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    {
+        cudaError_t ce = cudaSetDevice(dev);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) {
+            setLastError(std::string("gk_create: ") + cudaGetErrorString(ce));
+            c.stream = nullptr;
+            delete h;
+            return GK_ERR_CUDA;
+        }
+    }
     GkStatus s = allocFrameResources(c);
     if (s != GK_OK) {
         gk_destroy(h);
@@ -425,6 +447,10 @@ GkStatus gk_upload_plane(GkContext* ctx, GkPlane plane, const void* src, size_t 
         return GK_ERR_INVALID_ARGUMENT;
     }
     applyPendingHistorySwap(c);
+    {
+        const void* bufs[] = {c.planes.p[plane]};
+        waitAsyncCopyBeforeWriting(c, bufs, 1); // an asynchronous read-back may still be reading this plane
+    }
     GK_CUDA(cudaMemcpyAsync(c.planes.p[plane], src, bytes, cudaMemcpyHostToDevice, c.stream));
     GK_CUDA(cudaStreamSynchronize(c.stream));
     return GK_OK;
@@ -567,13 +593,17 @@ GkStatus gk_set_option(GkContext* ctx, const char* name, double value)
     GK_CHECK_CTX(ctx);
     if (!name) return GK_ERR_INVALID_ARGUMENT;
     const std::string n(name);
-    if (n == "trace_variant") c.traceVariant = (int)value;
+    if (n == "trace_variant") {
+        c.traceVariant = (int)value;
+        c.coopThreshold = c.traceVariant == 1 ? 262144u : 65536u; // measured optimum of each wave loop
+    }
     else if (n == "sched_refill_min") c.schedRefillMin = (uint32_t)std::min(32.0, std::max(1.0, value));
     else if (n == "sched_bias_node") c.schedBiasN = (uint32_t)std::max(0.0, value);
     else if (n == "sched_min_rays") c.schedMinRays = (uint32_t)std::max(0.0, value);
     else if (n == "sched_keep_node") c.schedKeepN = (uint32_t)std::min(33.0, std::max(1.0, value));
     else if (n == "sched_keep_tri") c.schedKeepT = (uint32_t)std::min(33.0, std::max(1.0, value));
     else if (n == "coop_threshold") c.coopThreshold = (uint32_t)std::max(0.0, value);
+    else if (n == "primary_lane_kernel") c.primaryLaneKernel = value != 0;
     else if (n == "tail_threshold") c.tailThreshold = (uint32_t)std::max(0.0, value);
     else if (n == "tail_fraction") c.tailFraction = (float)value;
     else if (n == "concurrent_shadow") c.concurrentShadow = value != 0;
@@ -582,6 +612,44 @@ GkStatus gk_set_option(GkContext* ctx, const char* name, double value)
         setLastError("gk_set_option: unknown option '" + n + "'");
         return GK_ERR_INVALID_ARGUMENT;
     }
+    return GK_OK;
+}
+
+GkStatus gk_measure_read_bandwidth(GkContext* ctx, size_t bytes, int reps, float* out_gbps)
+{
+    GK_CHECK_CTX(ctx);
+    if (!out_gbps || bytes < (1u << 20) || reps < 1) {
+        setLastError("gk_measure_read_bandwidth: bytes >= 1 MiB, reps >= 1");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    DevBuf<uint4> buf;
+    const size_t n16 = bytes / 16;
+    GK_CUDA(buf.reserve(n16 + 1));
+    GK_CUDA(cudaMemsetAsync(buf.p, 0x5a, n16 * 16, c.stream));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+    const unsigned grid = (unsigned)sms * 8u;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    k_stream_read<<<grid, 256, 0, c.stream>>>(buf.p, n16, 2, buf.p + n16); // warm-up: brings the buffer into L2 when it fits
+    float best = 0.f;
+    for (int k = 0; k < 5; ++k) {
+        cudaEventRecord(e0, c.stream);
+        k_stream_read<<<grid, 256, 0, c.stream>>>(buf.p, n16, reps, buf.p + n16);
+        cudaEventRecord(e1, c.stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0), cudaEventDestroy(e1), buf.release();
+            setLastError(std::string("gk_measure_read_bandwidth: ") + cudaGetErrorString(e));
+            return GK_ERR_CUDA;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms > 0) best = std::max(best, (float)((double)n16 * 16.0 * reps / (ms * 1e-3) / 1e9));
+    }
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    buf.release();
+    *out_gbps = best;
     return GK_OK;
 }
 

@@ -1071,8 +1071,8 @@ GkStatus buildBlasForest(Context& c)
         setLastError("too many models");
         return GK_ERR_UNSUPPORTED;
     }
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    ScopedEvents evs(2);
+    cudaEvent_t e0 = evs.e[0], e1 = evs.e[1];
     cudaEventRecord(e0, st);
     const bool ploc = c.blasPloc && T.n > 2;
     GkStatus s = buildRadixTree(c, T, T.group.p, groups, 64, 0, !ploc);
@@ -1094,7 +1094,6 @@ GkStatus buildBlasForest(Context& c)
     GK_CUDA(cudaMemcpyAsync(c.models.data(), c.dModels.p, sizeof(ModelInfo) * groups, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&c.msBlasBuild, e0, e1);
-    cudaEventDestroy(e0), cudaEventDestroy(e1);
     rootRef.release();
     return GK_OK;
 }
@@ -1112,8 +1111,8 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
     }
     Lbvh& T = c.tlasTree;
     if (refit && (!c.haveInstances || count != T.n)) refit = false;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    ScopedEvents evs(2);
+    cudaEvent_t e0 = evs.e[0], e1 = evs.e[1];
     cudaEventRecord(e0, st);
     GK_CUDA(c.dNodes.reserve(count));
     GK_CUDA(cudaMemcpyAsync(c.dNodes.p, nodes, sizeof(GkNodeProxy) * count, cudaMemcpyHostToDevice, st));
@@ -1185,7 +1184,6 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
     cudaEventElapsedTime(&ms, e0, e1);
     if (refit) c.msRefit = ms; else c.msTlasBuild = ms;
     c.stats.msBvh = ms;
-    cudaEventDestroy(e0), cudaEventDestroy(e1);
     c.haveInstances = true;
     return GK_OK;
 }

@@ -23,6 +23,19 @@ void setLastError(const std::string& s);
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t cap = 0; // elements
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr, o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept
+    {
+        if (this != &o) {
+            release();
+            p = o.p, cap = o.cap, o.p = nullptr, o.cap = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); } // temporaries in entry points are freed on every return path
     cudaError_t reserve(size_t n)
     {
         if (n <= cap) return cudaSuccess;
@@ -39,6 +52,22 @@ template <class T> struct DevBuf {
         p = nullptr, cap = 0;
     }
     size_t bytes() const { return cap * sizeof(T); }
+};
+
+// Timing events that are destroyed on every return path.
+struct ScopedEvents {
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    explicit ScopedEvents(int n)
+    {
+        for (int i = 0; i < n && i < 4; ++i) cudaEventCreate(&e[i]);
+    }
+    ~ScopedEvents()
+    {
+        for (cudaEvent_t x : e)
+            if (x) cudaEventDestroy(x);
+    }
+    ScopedEvents(const ScopedEvents&) = delete;
+    ScopedEvents& operator=(const ScopedEvents&) = delete;
 };
 
 // Binary radix tree (Karras 2012) over `n` primitives, kept for refit.
@@ -167,7 +196,7 @@ struct Context {
     uint32_t tailThreshold = 0;     // finish the frame in one launch once this few paths are alive (0: never)
     bool travStats = false;
     uint32_t blasLeafMax = 4;       // triangles per BLAS leaf (<= kBlasLeafMax)
-    uint32_t coopThreshold = 65536; // waves smaller than this use the 8-lanes-per-ray traversal
+    uint32_t coopThreshold = 262144; // waves smaller than this use the 8-lanes-per-ray traversal (variant 0: measured optimum 65536, set by gk_create)
     GkFrameStats stats{};
     cudaEvent_t evA = nullptr, evB = nullptr;
     std::vector<cudaEvent_t> evPool;
@@ -206,10 +235,11 @@ struct Context {
     bool sahCollapse = true;        // cost-driven wide collapse (false: greedy by surface area)
     // scheduled traversal kernel (gk_trace_sched.cuh)
     int traceVariant = 1;            // 0: while-while lane kernel / cooperative kernel, 1: persistent vote-scheduled kernel
-    uint32_t schedRefillMin = 8;     // refill a warp's idle lanes once this many rays have finished
+    uint32_t schedRefillMin = 6;     // refill a warp's idle lanes once this many rays have finished
     uint32_t schedBiasN = 0;         // vote bias towards the node step (lanes)
     uint32_t schedKeepN = 12;        // a node phase goes on while this many lanes hold a node (33: one step per vote)
-    uint32_t schedKeepT = 10;        // ditto for the triangle phase
+    uint32_t schedKeepT = 4;         // ditto for the triangle phase
+    bool primaryLaneKernel = true;   // wave 0 (coherent camera rays) on the while-while lane kernel
     uint32_t schedMinRays = 0;       // waves smaller than this keep the variant-0 kernels
     int schedBlocksPerSm = 0, smCount = 0;
     static constexpr uint32_t kCursorCount = 1024;

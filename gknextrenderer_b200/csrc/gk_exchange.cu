@@ -399,6 +399,11 @@ GkStatus exchangePack(Context& c, void* dStaging)
 
 GkStatus exchangeUnpack(Context& c, const void* dAll)
 {
+    {   // the six exchange planes are about to be overwritten: an asynchronous read-back may still be reading one of them
+        const void* bufs[] = {c.planes.p[GK_PLANE_OUTPUT_DIFFUSE], c.planes.p[GK_PLANE_OUTPUT_SPECULAR], c.planes.p[GK_PLANE_ALBEDO], c.planes.p[GK_PLANE_NORMAL],
+                              c.planes.p[GK_PLANE_OBJECT_ID0], c.planes.p[GK_PLANE_MOTION]};
+        waitAsyncCopyBeforeWriting(c, bufs, 6);
+    }
     const ExchangeArgs A = makeArgs(c);
     const unsigned grid = (unsigned)std::min<uint64_t>((A.rankWords * c.tileCount + 255) / 256, 148u * 16u);
     k_exchange<false><<<grid, 256, 0, c.stream>>>(A, (uint32_t*)dAll, 0, c.tileCount);

@@ -368,6 +368,12 @@ GkStatus filterFrameOwnedRows(Context& c)
         setLastError("gk_filter_frame_owned: needs ProgressiveRender != 0 and BFSize == 0 (the spatial passes read rows of other ranks)");
         return GK_ERR_UNSUPPORTED;
     }
+    // the selection outline (DenoiseJBF:55-68, 173-179) reads object ids at y +- 1, i.e. rows of other ranks on tile borders, which
+    // are neither traced nor exchanged in this mode: only "nothing selected" composes correctly on owned rows alone
+    if (c.haveUbo && c.tileCount > 1 && c.ubo.SelectedId != 0xFFFFFFFFu) {
+        setLastError("gk_filter_frame_owned: SelectedId must be 0xFFFFFFFF (the selection outline reads object ids of neighbouring rows owned by other ranks)");
+        return GK_ERR_UNSUPPORTED;
+    }
     return runFilters(c, true);
 }
 
@@ -385,8 +391,8 @@ static GkStatus runFilters(Context& c, bool ownedRowsOnly)
     }
     c.tracedSinceFilter = false;
     GK_CUDA(cudaMemcpyAsync(c.dUbo, &c.ubo, sizeof(GkUniformBufferObject), cudaMemcpyHostToDevice, st));
-    cudaEvent_t e0, e1, e2;
-    cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventCreate(&e2);
+    ScopedEvents evs(3);
+    cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], e2 = evs.e[2];
     void** P = c.planes.p;
     ReprojectArgs R;
     R.src[0] = (const uint2*)P[GK_PLANE_OUTPUT_DIFFUSE], R.src[1] = (const uint2*)P[GK_PLANE_OUTPUT_SPECULAR], R.src[2] = (const uint2*)P[GK_PLANE_ALBEDO];
@@ -410,7 +416,6 @@ static GkStatus runFilters(Context& c, bool ownedRowsOnly)
     GK_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&c.stats.msReproject, e0, e1);
     cudaEventElapsedTime(&c.stats.msDenoise, e1, e2);
-    cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(e2);
     c.stats.launches += 2;
     // "copy pass": the accumulated images become next frame's history and ObjectId0 becomes
     // ObjectId1.  No bytes move: the plane pointers are exchanged when the next frame starts

@@ -239,9 +239,14 @@ GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out);
 GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out);
 /* Tuning hooks (the defaults are the measured optima; DESIGN.md lists the sweeps).  Unknown names return
  * GK_ERR_INVALID_ARGUMENT.  Names: "trace_variant" (0 while-while lane kernel + cooperative kernel, 1 persistent
- * vote-scheduled kernel), "sched_refill_min", "sched_bias_node", "sched_keep_node", "sched_keep_tri", "sched_min_rays", "coop_threshold", "tail_threshold",
+ * vote-scheduled kernel), "sched_refill_min", "sched_bias_node", "sched_keep_node", "sched_keep_tri", "sched_min_rays", "coop_threshold", "primary_lane_kernel", "tail_threshold",
  * "tail_fraction", "concurrent_shadow", "wave_lookahead". */
 GkStatus gk_set_option(GkContext* ctx, const char* name, double value);
+/* Measurement aid for the roofline of the traversal kernels ("peak measured once with an L2-resident
+ * stream microbench, not assumed"): streams 128-bit loads that bypass L1 over a scratch buffer of `bytes`, `reps` times
+ * per launch, and returns the best GB/s of five launches.  bytes well below the 126 MB L2 measures L2 read bandwidth,
+ * bytes far above it measures HBM read bandwidth. */
+GkStatus gk_measure_read_bandwidth(GkContext* ctx, size_t bytes, int reps, float* out_gbps);
 /* Enables node-visit / triangle-test counters in the traversal kernels (slower). */
 GkStatus gk_set_traversal_stats(GkContext* ctx, int enabled);
 /* CUDA stream used by the context (cudaStream_t), for callers that order their own work. */

@@ -6,6 +6,7 @@
 #include "orc_scene.h"
 #include <chrono>
 #include <thread>
+#include <vector>
 
 using namespace orc;
 
@@ -61,10 +62,9 @@ double orc_intersect(void* h, const float* rays, uint32_t n, float* out_tuv, uin
 // Brute-force closest hit over every triangle of every ray-visible instance with the same
 // per-triangle arithmetic: independent of any BVH, used to classify id mismatches
 // (exact-t tie vs. a box test that dropped the true nearest triangle).
-void orc_intersect_bruteforce(void* h, const float* rays, uint32_t n, float* out_tuv, uint32_t* out_ids)
+static void bruteforceRange(const Scene* S, const float* rays, uint32_t lo, uint32_t hi, float* out_tuv, uint32_t* out_ids)
 {
-    const Scene* S = (const Scene*)h;
-    for (uint32_t i = 0; i < n; ++i) {
+    for (uint32_t i = lo; i < hi; ++i) {
         const float* r = rays + 8 * (size_t)i;
         RayQ q = makeRay(f3(r[0], r[1], r[2]), f3(r[4], r[5], r[6]), r[3], r[7]);
         Hit best = q.hit;
@@ -92,6 +92,24 @@ void orc_intersect_bruteforce(void* h, const float* rays, uint32_t n, float* out
         out_tuv[3 * (size_t)i] = best.t, out_tuv[3 * (size_t)i + 1] = best.u, out_tuv[3 * (size_t)i + 2] = best.v;
         out_ids[2 * (size_t)i] = bestNode == 0xffffffffu ? 0xffffffffu : best.prim, out_ids[2 * (size_t)i + 1] = bestNode;
     }
+}
+
+void orc_intersect_bruteforce_mt(void* h, const float* rays, uint32_t n, float* out_tuv, uint32_t* out_ids, int threads)
+{
+    const Scene* S = (const Scene*)h;
+    if (threads < 1) threads = 1;
+    if ((uint32_t)threads > n) threads = (int)(n ? n : 1);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        const uint32_t lo = (uint32_t)((uint64_t)n * t / threads), hi = (uint32_t)((uint64_t)n * (t + 1) / threads);
+        pool.emplace_back(bruteforceRange, S, rays, lo, hi, out_tuv, out_ids);
+    }
+    for (auto& th : pool) th.join();
+}
+
+void orc_intersect_bruteforce(void* h, const float* rays, uint32_t n, float* out_tuv, uint32_t* out_ids)
+{
+    bruteforceRange((const Scene*)h, rays, 0, n, out_tuv, out_ids);
 }
 
 void orc_raycast(void* h, const float* origin_dir /* 6 floats per ray */, uint32_t n, GkRayCastResult* out)

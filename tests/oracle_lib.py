@@ -32,6 +32,7 @@ def load_oracle():
     lib.orc_intersect.restype = C.c_double
     lib.orc_intersect.argtypes = [_P, _P, C.c_uint32, _P, _P, C.c_int, _P]
     lib.orc_intersect_bruteforce.argtypes = [_P, _P, C.c_uint32, _P, _P]
+    lib.orc_intersect_bruteforce_mt.argtypes = [_P, _P, C.c_uint32, _P, _P, C.c_int]
     lib.orc_raycast.argtypes = [_P, _P, C.c_uint32, _P]
     lib.orc_blas_node_count.restype = C.c_uint32
     lib.orc_blas_node_count.argtypes = [_P, C.c_uint32]
@@ -114,12 +115,13 @@ class OracleScene:
         self.last_stats = st
         return tuv, ids
 
-    def intersect_bruteforce(self, rays: np.ndarray):
+    def intersect_bruteforce(self, rays: np.ndarray, threads=None):
+        """Exhaustive closest hit (no BVH): every triangle of every instance, the reference's per-triangle arithmetic."""
         rays = np.ascontiguousarray(rays, np.float32)
         n = rays.shape[0]
         tuv = np.empty((n, 3), np.float32)
         ids = np.empty((n, 2), np.uint32)
-        self.lib.orc_intersect_bruteforce(self.h, ptr(rays), n, ptr(tuv), ptr(ids))
+        self.lib.orc_intersect_bruteforce_mt(self.h, ptr(rays), n, ptr(tuv), ptr(ids), threads or (os.cpu_count() or 1))
         return tuv, ids
 
     def raycast(self, origin_dir: np.ndarray):
@@ -128,14 +130,6 @@ class OracleScene:
         out = (GkRayCastResult * od.shape[0])()
         self.lib.orc_raycast(self.h, ptr(od), od.shape[0], out)
         return out
-
-    def nodes_dump(self):
-        """(list of per-BLAS node arrays, TLAS node array), each (n, 8) float32 words."""
-        pre = "ref" if self.use_ref else "orc"
-        out = []
-        m = 0
-        # number of models is not exported; probe until the caller-supplied count
-        return pre, out, m
 
     def render(self, ubo, width, height, threads=8, cubes=None, voxels=None):
         px = width * height

@@ -58,7 +58,11 @@ def _random_rays(rng, n, lo, hi, tmax=1000.0, tmin=1e-3):
     return r
 
 
-TIE_EPS = 2.0 ** -21  # ids may differ only where both distances agree to 4 ulp (coplanar / shared-edge hits)
+# ids may differ only where both distances agree to 16 ulp AND the GPU's is not the farther one (coplanar / shared-edge hits).
+# tinybvh culls a node when its slab entry (bmin - O) * rD, rounded per operation, is not below the current hit distance; that
+# product carries an error of a few ulp of t, so between two surfaces a few ulp apart it can keep the farther one (seen on the
+# city at t = 787 m: 12 ulp).  Every such ray is checked against the brute-force nearest hit (no BVH) below.
+TIE_EPS = 2.0 ** -19
 
 
 def _classify(g_tuv, g_ids, o_tuv, o_ids, label):
@@ -98,18 +102,37 @@ def _compare_hits(r, orc, rays, label, max_tie_fraction=2e-3):
     return max(ties, _compare_with(r, orc, rays, o_tuv, o_ids, label, max_tie_fraction))
 
 
+REFERENCE_MISS_FRACTION = 1e-3  # rays on which the reference's own BVH culls the true nearest triangle (see _compare_with)
+PARITY_LOG = []                 # one record per comparison; test_zz_write_parity_log dumps it for profiles/
+
+
 def _compare_with(r, orc, rays, o_tuv, o_ids, label, max_tie_fraction):
+    """Classes of rays whose ids differ from the CPU query's:
+      exact-t tie ...... same distance bits, two coincident surfaces (touching bricks, a box standing on the floor)
+      epsilon tie ...... distances within TIE_EPS, the GPU's not the farther one
+      reference miss ... the GPU hit is CLOSER by more than that.  tinybvh's slab test (tiny_bvh.h:6920-6932) rounds
+                         (bmin - O) * rD per operation; a ray that grazes a box edge (camera rays at 45 degrees to
+                         axis-aligned bricks hit face diagonals and box edges exactly) can get tmax < tmin by an ulp and the
+                         box - with the nearest triangle in it - is culled.  Such rays are only accepted when the GPU hit is
+                         bit-equal to the exhaustive search over every triangle (no BVH), checked on a sample, and rare.
+      error ............ anything else (GPU farther than the reference, or not the exhaustive nearest): none allowed."""
     g_tuv, g_ids = r.intersect(rays)
     differ, exact, eps, hard = _classify(g_tuv, g_ids, o_tuv, o_ids, label)
-    assert hard.sum() == 0, f"{label}: {int(hard.sum())} rays hit a different triangle at a different distance: first {np.nonzero(hard)[0][:5]}"
-    assert differ.sum() <= max(2, int(max_tie_fraction * len(rays))), f"{label}: too many ties ({int(differ.sum())})"
-    if eps.any():  # epsilon ties must be the true nearest hit: check against brute force (no BVH at all)
-        idx = np.nonzero(eps)[0][:64]
-        b_tuv, b_ids = orc.intersect_bruteforce(rays[idx])
-        assert np.array_equal(_bits(b_tuv[:, 0]), _bits(g_tuv[idx, 0])), f"{label}: epsilon ties are not the brute-force nearest hit"
+    closer = hard & (g_tuv[:, 0] < o_tuv[:, 0])
+    errors = hard & ~closer
+    assert errors.sum() == 0, f"{label}: {int(errors.sum())} rays where the GPU hit is farther than the reference's: first {np.nonzero(errors)[0][:5]}"
+    for mask, what in ((closer, "reference misses"), (eps, "epsilon ties")):
+        if mask.any():  # must be the true nearest hit: exhaustive search, same per-triangle arithmetic
+            idx = np.nonzero(mask)[0][:48]
+            b_tuv, b_ids = orc.intersect_bruteforce(rays[idx])
+            assert np.array_equal(_bits(b_tuv[:, 0]), _bits(g_tuv[idx, 0])), f"{label}: {what} are not the brute-force nearest hit"
+    assert closer.sum() <= max(1, int(REFERENCE_MISS_FRACTION * len(rays))), f"{label}: too many reference misses ({int(closer.sum())})"
+    assert (exact | eps).sum() <= max(2, int(max_tie_fraction * len(rays))), f"{label}: too many ties ({int((exact | eps).sum())})"
     same = ~differ
     assert np.array_equal(_bits(g_tuv[same]), _bits(o_tuv[same])), f"{label}: t/u/v not bit-identical"
-    return int(differ.sum())
+    PARITY_LOG.append({"case": label, "rays": int(len(rays)), "id_equal_tuv_bit_equal": int(same.sum()), "exact_t_ties": int(exact.sum()),
+                       "eps_ties": int(eps.sum()), "reference_misses_gpu_is_bruteforce_nearest": int(closer.sum()), "errors": int(errors.sum())})
+    return int((exact | eps).sum())
 
 
 def test_primary_hit_ids_cornell_640x360_bit_exact(built):
@@ -361,13 +384,14 @@ def test_config3_bricks_200k_instances_after_rebuild(built):
     eng, r, orc, (nodes, n) = _setup("bricks", W, H, (200000, 42))
     rng = np.random.default_rng(23)
     rays = np.concatenate([_subsampled_primary(eng, W, H, 5), _random_rays(rng, 300000, (-20, 0.0, -20), (20, 3.0, 20))])
-    _compare_hits(r, orc, rays, "C3 bricks 200k build")
+    # touching bricks share coplanar faces: 1-2 % of the rays end on a two-surface tie
+    _compare_hits(r, orc, rays, "C3 bricks 200k build", max_tie_fraction=3e-2)
     eng.step_scene(1)
     nodes, n = eng.update_nodes()
     r.update_instances(nodes, n, refit=False)
     orc.set_nodes(nodes, n)
     _attach_reference(orc, eng, nodes, n)
-    _compare_hits(r, orc, rays, "C3 bricks 200k after a step (rebuilt)")
+    _compare_hits(r, orc, rays, "C3 bricks 200k after a step (rebuilt)", max_tie_fraction=3e-2)
 
 
 # ---------------------------------------------------------------- filters
@@ -669,3 +693,13 @@ def test_api_misuse_fails_loudly(built):
     r.set_ubo(eng.ubo(48, 40))
     r.render_frame()
     assert r.readback("DENOISED").shape == (40, 48, 4)
+
+
+def test_zz_write_parity_log(built):
+    """Writes the tie / reference-miss counts of this run (gpurun_out/parity_cases.json; copied to profiles/)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity_cases.json"), "w") as f:
+        json.dump(PARITY_LOG, f, indent=1)
+    assert all(c["errors"] == 0 for c in PARITY_LOG)
