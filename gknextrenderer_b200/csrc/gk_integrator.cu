@@ -674,8 +674,9 @@ __global__ void k_wave_end(const uint32_t* __restrict__ nextE, const uint32_t* _
 // (trace -> shade -> trace ...), one path per lane, instead of paying three launches and a queue
 // count read-back per wave.  counters[0] / [1] receive the extension / shadow rays traced here.
 __global__ void __launch_bounds__(128, 4) k_tail(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, SceneView V, ShadeScene SS, PathState S, PlaneView PL,
-                                                 RayQueue inE, uint32_t countE, RayQueue inS, uint32_t countS, unsigned long long* __restrict__ counters)
+                                                 RayQueue inE, uint32_t countE, RayQueue inS, uint32_t countS, unsigned long long* __restrict__ counters, int countsOnDevice)
 {
+    if (countsOnDevice) countE = *inE.count, countS = *inS.count; // streamed wave loop: the host only knows an upper bound (it sized the grid)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nE = 0, nS = 0;
     if (i < countE + countS) {
@@ -1021,13 +1022,15 @@ static GkStatus traceFrameStreamed(Context& c)
     uint32_t bound = n;      // upper bound of the rays of the wave being enqueued (paths alive never increase)
     uint32_t enqueued = 0;   // waves enqueued so far
     uint32_t known = 0;      // slots read so far: slot w holds the queue sizes of wave w + 1
-    bool drained = false;
+    bool drained = false, tailRan = false;
+    size_t tailSpan[2] = {0, 0};
     auto consume = [&](uint32_t upTo) -> GkStatus { // reads slots [known, upTo)
         for (; known < upTo; ++known) {
             uint32_t e = 0, s2 = 0;
             const GkStatus r = waitWaveSlot(c, known, tag, e, s2);
             if (r != GK_OK) return r;
-            fs.extensionRays += e, fs.shadowRays += s2;
+            // the rays the tail launch starts from are counted by the tail itself (it counts every ray it traces)
+            if (!(tailRan && known + 1 == enqueued)) fs.extensionRays += e, fs.shadowRays += s2;
             if (e + s2) fs.waves = known + 2;
             else drained = true;
             bound = e + s2;
@@ -1043,6 +1046,20 @@ static GkStatus traceFrameStreamed(Context& c)
         }
         const int cur = (int)(wave & 1u), nxt = cur ^ 1;
         const uint32_t sizeE = wave == 0 ? n : bound, sizeS = wave == 0 ? 0u : bound;
+        if (wave > 0 && bound <= c.streamTailPaths && c.captureWave < 0 && !c.travStats) {
+            // a handful of long paths is left (dielectric primaries run to MaxNumberOfBounces): one launch walks each of them to
+            // its end (trace -> shade -> trace ..., one path per lane) instead of a dozen waves of a few rays at ~65 us each
+            const size_t ta = mark();
+            GK_CUDA(cudaMemsetAsync(c.dTailCounters, 0, 3 * sizeof(unsigned long long), st));
+            k_tail<<<gridFor((size_t)2 * bound, 128), 128, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], 0, c.shadowQ[cur], 0, c.dTailCounters, 1);
+            fs.launches++;
+            const size_t tb = mark();
+            tailSpan[0] = ta, tailSpan[1] = tb;
+            GK_CUDA(cudaMemcpyAsync((void*)(c.hCounts + 2), c.dTailCounters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            fs.tailPaths = bound;
+            tailRan = true;
+            break;
+        }
         const size_t a = mark();
         if ((int)wave == c.captureWave && look == 0) {
             const uint32_t countE = wave == 0 ? n : c.hWave[4 * (size_t)(wave - 1)];
@@ -1105,7 +1122,7 @@ static GkStatus traceFrameStreamed(Context& c)
         const GkStatus r = consume(enqueued);
         if (r != GK_OK) return r;
     }
-    if (!drained) {
+    if (!drained && !tailRan) {
         GK_CUDA(cudaStreamSynchronize(st));
         setLastError("gk_trace_frame: paths were still alive after the wave limit (" + std::to_string(Context::kWaveLimit) + "); lower NumberOfSamples / bounces");
         return GK_ERR_UNSUPPORTED;
@@ -1129,7 +1146,19 @@ static GkStatus traceFrameStreamed(Context& c)
         else fs.msAccumulate += ms;
     }
     cudaEventElapsedTime(&fs.msTotal, c.evPool[evStart], c.evPool[hEnd]);
-    if (getenv("GK_WAVE_LOG")) { // per-wave device times (diagnostics): trace span, shade span, queue sizes
+    if (tailRan) {
+        cudaEventElapsedTime(&fs.msTail, c.evPool[tailSpan[0]], c.evPool[tailSpan[1]]);
+        unsigned long long t[3];
+        memcpy(t, (const void*)(c.hCounts + 2), sizeof(t));
+        if (t[2]) {
+            setLastError("gk_trace_frame: paths were still alive when the tail kernel's step guard (65536) expired; lower NumberOfSamples / bounces");
+            return GK_ERR_UNSUPPORTED;
+        }
+        fs.extensionRays += t[0], fs.shadowRays += t[1];
+        fs.tailExtensionRays = t[0], fs.tailShadowRays = t[1];
+    }
+    if (getenv("GK_WAVE_LOG")) {
+        if (tailRan) fprintf(stderr, "[gk tail] %u paths (bound)  %.3f ms  extension %llu shadow %llu rays\n", fs.tailPaths, fs.msTail, (unsigned long long)fs.tailExtensionRays, (unsigned long long)fs.tailShadowRays); // per-wave device times (diagnostics): trace span, shade span, queue sizes
         size_t k = 1;
         for (uint32_t w = 0; w < enqueued && k + 2 < spans.size(); ++w, k += 4) {
             float tr = 0, sh = 0;
@@ -1223,7 +1252,7 @@ GkStatus traceFrame(Context& c)
             // few paths left: finish them in one launch
             const size_t a = mark();
             GK_CUDA(cudaMemsetAsync(c.dTailCounters, 0, 3 * sizeof(unsigned long long), st));
-            k_tail<<<gridFor((size_t)countE + countS, 128), 128, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.dTailCounters);
+            k_tail<<<gridFor((size_t)countE + countS, 128), 128, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], countE, c.shadowQ[cur], countS, c.dTailCounters, 0);
             fs.launches++;
             const size_t b = mark();
             spans.push_back({a, b, 5});
