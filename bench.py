@@ -177,6 +177,12 @@ def main():
     import gknextrenderer_b200 as gk
     from gknextrenderer_b200 import compositor as comp
 
+    verbose = bool(os.environ.get("GK_BENCH_VERBOSE"))
+
+    def stage(msg):
+        if verbose:
+            print(f"[bench rank {rank} {time.perf_counter():.3f}] {msg}", file=sys.stderr, flush=True)
+
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
@@ -279,12 +285,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up
+    stage("scene loaded, warm-up")
     n_warm = max(3, args.warmup)
     for i in range(n_warm):
         frame(i)
     info = r.bvh_info()
 
     # ---- timed: device-resident inputs
+    stage("timed region (device-resident)")
     sampler = ClockSampler(local_rank) if rank == 0 else None  # started before the barrier: NVML start-up must not delay rank 0 inside the timed region
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -311,6 +319,7 @@ def main():
     # ---- timed: end to end through the renderer interface, host UBO in, final image out
     # the final image of every step is read back into one of two pinned buffers; the copy runs on the
     # library's copy stream and overlaps the next step (gk_readback_async), the last one is waited for
+    stage("timed region (end to end)")
     final_host = [torch.empty((H, W, 4), dtype=torch.float16).pin_memory() for _ in range(2)]
     fin_bytes = r.plane_bytes("DENOISED")
     for i in range(2):
@@ -334,6 +343,7 @@ def main():
     h2d = 784 + (info.instanceCount * 208 if dynamic else 0)
     d2h = fin_bytes
 
+    stage("reduce over ranks")
     # ---- reduce over ranks: max time, summed rays
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
@@ -359,6 +369,7 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    stage("roofline probes (rank 0)")
     # ---- roofline of the dominant kernel (traversal).  SURVEY.md 8(d): L2 / SM-issue bound; algorithmic bytes per ray =
     #      48 (ray in + hit out) + 80 x node visits + 48 x triangle tests, the visits counted by an instrumented frame.
     r.set_traversal_stats(True)

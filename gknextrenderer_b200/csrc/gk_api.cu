@@ -605,6 +605,7 @@ GkStatus gk_set_option(GkContext* ctx, const char* name, double value)
     else if (n == "coop_threshold") c.coopThreshold = (uint32_t)std::max(0.0, value);
     else if (n == "primary_lane_kernel") c.primaryLaneKernel = value != 0;
     else if (n == "stream_tail_paths") c.streamTailPaths = (uint32_t)std::max(0.0, value);
+    else if (n == "tail_coop") c.tailCoop = value != 0;
     else if (n == "tail_threshold") c.tailThreshold = (uint32_t)std::max(0.0, value);
     else if (n == "tail_fraction") c.tailFraction = (float)value;
     else if (n == "concurrent_shadow") c.concurrentShadow = value != 0;

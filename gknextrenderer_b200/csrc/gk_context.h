@@ -240,7 +240,8 @@ struct Context {
     uint32_t schedKeepN = 12;        // a node phase goes on while this many lanes hold a node (33: one step per vote)
     uint32_t schedKeepT = 4;         // ditto for the triangle phase
     bool primaryLaneKernel = true;   // wave 0 (coherent camera rays) on the while-while lane kernel
-    uint32_t streamTailPaths = 4096; // streamed wave loop: finish the frame in one k_tail launch once at most this many rays are in flight
+    bool tailCoop = true;            // ... with eight lanes per path (k_tail_coop) instead of one
+    uint32_t streamTailPaths = 262144; // streamed wave loop: finish the frame in one k_tail launch once at most this many rays are in flight
     uint32_t schedMinRays = 0;       // waves smaller than this keep the variant-0 kernels
     int schedBlocksPerSm = 0, smCount = 0;
     static constexpr uint32_t kCursorCount = 1024;

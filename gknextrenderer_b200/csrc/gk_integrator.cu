@@ -714,6 +714,56 @@ __global__ void __launch_bounds__(128, 4) k_tail(const GkUniformBufferObject* __
     }
 }
 
+// The same tail with eight lanes per path: what is left at the end of a frame is a few hundred long paths (dielectric
+// primaries run to MaxNumberOfBounces) whose rays depend on one another, so the launch is bound by the latency of a single
+// ray.  The cooperative traversal (lane j tests child j / triangle j) cuts that latency several times; lane 0 of a group runs
+// the path's state machine and hands the next ray to its group through shuffles.
+__global__ void __launch_bounds__(256, 2) k_tail_coop(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, SceneView V, ShadeScene SS, PathState S, PlaneView PL,
+                                                      RayQueue inE, RayQueue inS, unsigned long long* __restrict__ counters)
+{
+    __shared__ uint2 stack[kRaysPerBlock * kStackStride];
+    const uint32_t countE = *inE.count, countS = *inS.count;
+    const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, shift = lane & 24u;
+    const unsigned gmask = 0xffu << shift;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; // one group of eight lanes per queue entry
+    uint32_t nE = 0, nS = 0;
+    if (i < countE + countS) { // whole groups take the branch together
+        const bool fromExtend = i < countE;
+        const uint32_t slot = fromExtend ? i : i - countE;
+        const RayQueue& Q = fromExtend ? inE : inS;
+        const uint32_t path = Q.path[slot];
+        RegSrc r;
+        r.o = Q.o_tmin[slot], r.d = Q.d_tmax[slot];
+        int kind = fromExtend ? 1 : 2;
+        int guard = 0;
+        for (; guard < 65536 && kind != 0; ++guard) {
+            Hit h{r.d.w, 0.f, 0.f, kInvalid, kInvalid};
+            bool hit = false;
+            if (r.d.w > 0.0f) { // uniform within the group: every lane holds the same ray
+                const f3 O = mk3(r.o.x, r.o.y, r.o.z), dn = normalizeRayDir(mk3(r.d.x, r.d.y, r.d.z));
+                if (kind == 1) hit = traverseCoop<false, false>(V, O, dn, r.o.w, h, stackRowOf(stack), nullptr);
+                else hit = traverseCoop<true, false>(V, O, dn, r.o.w, h, stackRowOf(stack), nullptr);
+                if (sub == 0) (kind == 1 ? nE : nS)++;
+            }
+            Emit e;
+            e.kind = 0, e.o = e.d = mk3(0, 0, 0), e.tmin = e.tmax = 0.f;
+            if (sub == 0) {
+                r.tuvp = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+                r.inst = h.inst;
+                r.occ = hit;
+                shadePath(*ubo, P, SS, S, PL, path, r, e);
+            }
+            const int src = (int)shift; // lane 0 of the group
+            kind = __shfl_sync(gmask, e.kind, src);
+            r.o = make_float4(__shfl_sync(gmask, e.o.x, src), __shfl_sync(gmask, e.o.y, src), __shfl_sync(gmask, e.o.z, src), __shfl_sync(gmask, e.tmin, src));
+            r.d = make_float4(__shfl_sync(gmask, e.d.x, src), __shfl_sync(gmask, e.d.y, src), __shfl_sync(gmask, e.d.z, src), __shfl_sync(gmask, e.tmax, src));
+        }
+        if (kind != 0 && sub == 0) counters[2] = 1ull; // the step guard expired with the path still alive: the host reports it
+    }
+    if (nE) atomicAdd(&counters[0], (unsigned long long)nE);
+    if (nS) atomicAdd(&counters[1], (unsigned long long)nS);
+}
+
 // -------------------------------------------------------------------------------- accumulate
 // Core.PathTracing :88-100 — final stores of the pixel (RGBA16F render targets + fp32 parity copies)
 __global__ void __launch_bounds__(256) k_accumulate(FrameParams P, PathState S, PlaneView PL)
@@ -1051,7 +1101,8 @@ static GkStatus traceFrameStreamed(Context& c)
             // its end (trace -> shade -> trace ..., one path per lane) instead of a dozen waves of a few rays at ~65 us each
             const size_t ta = mark();
             GK_CUDA(cudaMemsetAsync(c.dTailCounters, 0, 3 * sizeof(unsigned long long), st));
-            k_tail<<<gridFor((size_t)2 * bound, 128), 128, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], 0, c.shadowQ[cur], 0, c.dTailCounters, 1);
+            if (c.tailCoop) k_tail_coop<<<gridFor((size_t)2 * bound * 8, 256), 256, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.dTailCounters);
+            else k_tail<<<gridFor((size_t)2 * bound, 128), 128, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], 0, c.shadowQ[cur], 0, c.dTailCounters, 1);
             fs.launches++;
             const size_t tb = mark();
             tailSpan[0] = ta, tailSpan[1] = tb;
