@@ -159,33 +159,71 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        scene_name, scene_args, W, H, settings = WORKLOADS[args.workload]
+        return reference_arm(args, scene_name, scene_args, W, H, settings)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    line = run(args, args.workload, args.shard, args.steps, args.warmup, rank, world, local_rank, secondary=False)
+    if world > 1 and args.workload == "room" and not os.environ.get("GK_BENCH_NO_SECONDARY"):
+        # BASELINE.json configs[3] (C4: 10M-triangle city, 3840x2160, progressive) on the same box in the same run: the
+        # north_star's ">= 7x at 8 GPUs on a 10M-triangle scene" is a statement about this workload, so its multi-GPU numbers
+        # are produced here, where the driver runs the scaling bench.  One GPU first (rank 0 alone), then all ranks, image tiles
+        # of one frame (strong scaling) and frame sharding (weak scaling: a step is `world` progressive frames).
+        sec = []
+        solo = run(args, "city", "tiles", 6, 3, rank, world, local_rank, secondary=True, solo=True)
+        for shard in ("tiles", "frames"):
+            res = run(args, "city", shard, 6, 3, rank, world, local_rank, secondary=True)
+            if rank == 0 and res is not None and solo is not None:
+                res["one_gpu_same_run"] = {"value": solo["value"], "ms_per_step": solo["ms_per_step"]}
+                res["speedup_vs_one_gpu_same_run"] = round(res["value"] / solo["value"], 3)
+                sec.append(res)
+        if rank == 0:
+            line["secondary"] = sec
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run(args, workload, shard, steps, warmup, rank, world, local_rank, secondary=False, solo=False):
+    """One workload through the timed regions; returns the result line on rank 0 (None elsewhere).  solo: rank 0 renders alone
+    (the 1-GPU figure of a multi-rank run), the other ranks wait at the closing barrier."""
+    import torch
+    import torch.distributed as dist
+    import gknextrenderer_b200 as gk
+    from gknextrenderer_b200 import compositor as comp
+
+    real_world = world
+    if solo:
+        if rank != 0:
+            dist.barrier()
+            return None
+        world = 1
+    args = argparse.Namespace(**vars(args))
+    args.workload, args.shard, args.steps, args.warmup = workload, shard, steps, warmup
     scene_name, scene_args, W, H, settings = WORKLOADS[args.workload]
     global TILE_ROWS
+    TILE_ROWS = 16
     if "GK_TILE_ROWS" in os.environ:
         TILE_ROWS = int(os.environ["GK_TILE_ROWS"])
     else:  # interleave finely enough that the rounding of tiles per rank stays below ~3 % of a rank's work
         while TILE_ROWS > 2 and H // (TILE_ROWS * world) < 32:
             TILE_ROWS //= 2
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        return reference_arm(args, scene_name, scene_args, W, H, settings)
-
-    import torch
-    import torch.distributed as dist
-    import gknextrenderer_b200 as gk
-    from gknextrenderer_b200 import compositor as comp
-
     verbose = bool(os.environ.get("GK_BENCH_VERBOSE"))
 
     def stage(msg):
         if verbose:
             print(f"[bench rank {rank} {time.perf_counter():.3f}] {msg}", file=sys.stderr, flush=True)
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
     # ---- the reference-facing path: Assets::Scene -> LogicRendererBase-shaped renderer -> C ABI
     eng = gk.Engine(scene_name, *scene_args)
@@ -361,13 +399,29 @@ def main():
         per_rank = None
         total_rays, total_rays_e2e, total_launches = float(agg["rays"]), float(rays_e2e), int(agg["launches"])
 
+    def release():
+        if world > 1:
+            comp.release(r)  # collective: unmap the peers before anyone frees its planes
+        r.h = None  # the context belongs to the host renderer
+        host.gkh_renderer_destroy(hr)
+        eng.close()
+
     if world > 1:
         dist.barrier()
     if rank != 0:
-        r.h = None
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        release()
+        return None
+    if secondary:
+        value = total_rays / (dev_ms * 1e-3) / 1e6
+        res = {"workload": WORKLOAD_NAMES[args.workload], "shard": "frames" if frame_shard else "tiles", "n_gpus": world, "value": round(value, 2), "unit": "Mrays/s",
+               "ms_per_step": round(dev_ms / args.steps, 4), "steps": args.steps, "warmup": n_warm, "scaling": "weak" if frame_shard else "strong",
+               "e2e": {"value": round(total_rays_e2e / (e2e_ms * 1e-3) / 1e6, 2), "ms_per_step": round(e2e_ms / args.steps, 4)},
+               "rays_per_step": round(total_rays / args.steps, 0), "per_rank_trace_ms": per_rank["trace_ms"] if per_rank else None, "exchange": exchange_mode,
+               "breakdown_ms_per_step": {k: round(agg[k] / args.steps, 4) for k in ("trace_kernels", "shade", "tail", "xchg", "rep", "jbf")}}
+        release()
+        if solo and real_world > 1:
+            dist.barrier()
+        return res
 
     stage("roofline probes (rank 0)")
     # ---- roofline of the dominant kernel (traversal).  SURVEY.md 8(d): L2 / SM-issue bound; algorithmic bytes per ray =
@@ -456,11 +510,8 @@ def main():
                 "wide_nodes_blas": int(info.blasNodes8), "wide_nodes_tlas": int(info.tlasNodes8), "bytes": int(info.bytesBvh + info.bytesGeometry)},
         "roofline": roofline, "roofline_filters": roofline_filters, "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
     }
-    print(json.dumps(line))
-    r.h = None  # the context belongs to the host renderer
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    release()
+    return line
 
 
 def _captured_sample(eng, r, frame_fn):

@@ -283,6 +283,9 @@ class Renderer:
     def exchange_push(self):
         self._check(self.lib.gk_exchange_push(self.h))
 
+    def exchange_close_peers(self):
+        self._check(self.lib.gk_exchange_close_peers(self.h))
+
     def stream(self) -> int:
         return int(self.lib.gk_stream(self.h) or 0)
 
@@ -305,6 +308,12 @@ class Renderer:
         out = (GkRayCastResult * n)()
         self._check(self.lib.gk_raycast(self.h, od.ctypes.data_as(C.c_void_p), n, out))
         return out
+
+    def raycast_task(self, io: np.ndarray):
+        """GPU ray-cast task (Task.RayCast.comp.slang) on an (n, 24) float32/uint32 view of RayCastIO records, in place."""
+        assert io.dtype.itemsize == 4 and io.shape[1] == 24 and io.flags["C_CONTIGUOUS"]
+        self._check(self.lib.gk_raycast_task(self.h, io.ctypes.data_as(C.c_void_p), io.shape[0]))
+        return io
 
     def set_ray_capture(self, wave: int):
         self._check(self.lib.gk_set_ray_capture(self.h, wave))

@@ -105,6 +105,17 @@ class GkRayCastResult(C.Structure):
 assert C.sizeof(GkRayCastResult) == 48
 
 
+class GkRayCastIn(C.Structure):
+    _fields_ = [("Origin", C.c_float * 4), ("Direction", C.c_float * 4), ("TMin", C.c_float), ("TMax", C.c_float), ("Reversed0", C.c_float), ("Reversed1", C.c_float)]
+
+
+class GkRayCastIO(C.Structure):
+    _fields_ = [("Context", GkRayCastIn), ("Result", GkRayCastResult)]
+
+
+assert C.sizeof(GkRayCastIO) == 96
+
+
 class GkConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32), ("tileIndex", C.c_uint32), ("tileCount", C.c_uint32),
                 ("tileRows", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32 * 6)]
@@ -145,6 +156,7 @@ CUDA_API = {
     "gk_trace_frame": (C.c_int, [_P]),
     "gk_filter_frame": (C.c_int, [_P]),
     "gk_raycast": (C.c_int, [_P, _P, C.c_uint32, _P]),
+    "gk_raycast_task": (C.c_int, [_P, _P, C.c_uint32]),
     "gk_intersect": (C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     "gk_intersect_device": (C.c_int, [_P, _P, C.c_uint32, _P, _P, C.c_int]),
     "gk_plane_bytes": (C.c_size_t, [_P, C.c_int]),
@@ -159,6 +171,7 @@ CUDA_API = {
     "gk_exchange_ipc_handles": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "gk_exchange_open_peers": (C.c_int, [_P, C.c_void_p, C.c_uint32]),
     "gk_exchange_push": (C.c_int, [_P]),
+    "gk_exchange_close_peers": (C.c_int, [_P]),
     "gk_frame_shard_handle": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "gk_frame_shard_open": (C.c_int, [_P, C.c_void_p, C.c_uint32]),
     "gk_frame_shard_push": (C.c_int, [_P]),

@@ -227,3 +227,20 @@ def composite_frame_shard(renderer, rank: int, world: int, dst_rank: int = 0, gr
     with torch.cuda.stream(stream):
         dist.all_reduce(token, group=group)  # the presenting rank holds the whole image
     return 3 * 8 * renderer.width * renderer.height * (world - 1) // world
+
+
+def release(renderer, group=None):
+    """Collective tear-down of the peer mappings of `renderer` (every rank calls it): unmap the peers' planes and gather
+    buffers, then wait for all ranks, so that no rank frees (gk_resize / gk_destroy) memory another rank still has mapped.
+    The exchange has to be enabled again afterwards."""
+    import torch.distributed as dist
+    hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    had = hkey in _p2p or hkey in _shard
+    _p2p.pop(hkey, None)
+    _shard.discard(hkey)
+    for k in [k for k in _staging if k[0] == hkey]:
+        _staging.pop(k, None)
+    if had:
+        renderer.exchange_close_peers()
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier(group=group)

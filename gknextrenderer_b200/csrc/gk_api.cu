@@ -1,6 +1,7 @@
 // gk_api.cu — the extern "C" entry points declared in include/gknext_cuda.h.
 // Each function's header comment there cites the reference interface it replaces.
 #include "gk_context.h"
+#include "gk_shading.cuh"
 #include <algorithm>
 #include <cstring>
 #include <new>
@@ -58,6 +59,38 @@ __global__ void __launch_bounds__(256) k_stream_read(const uint4* __restrict__ b
             acc.x ^= v.x, acc.y ^= v.y, acc.z ^= v.z, acc.w ^= v.w;
         }
     if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) *sink = acc; // keeps the loads alive
+}
+
+// Task.RayCast.comp.slang:31-55 — rays of the in-place records
+__global__ void k_task_pack(const GkRayCastIO* __restrict__ io, uint32_t n, float4* rays)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GkRayCastIn& c = io[i].Context;
+    rays[2 * i] = make_float4(c.Origin[0], c.Origin[1], c.Origin[2], kEps);          // ray.TMin = EPS (Shading.slang:712)
+    rays[2 * i + 1] = make_float4(c.Direction[0], c.Direction[1], c.Direction[2], 10000.0f); // TraceRay(..., 10000, ...)
+}
+
+// ... and the result half of the records (a miss only clears Hitted)
+__global__ void k_task_results(GkRayCastIO* __restrict__ io, const float* __restrict__ tuv, const uint32_t* __restrict__ ids, uint32_t n, ShadeScene SS)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GkRayCastIO& R = io[i];
+    const uint32_t node = ids[2 * i + 1], prim = ids[2 * i];
+    if (node == kInvalid) {
+        R.Result.Hitted = 0;
+        return;
+    }
+    const f3 ro = mk3(R.Context.Origin[0], R.Context.Origin[1], R.Context.Origin[2]), rd = mk3(R.Context.Direction[0], R.Context.Direction[1], R.Context.Direction[2]);
+    Vtx v;
+    resolveHit(SS, ro, rd, tuv[3 * i], tuv[3 * i + 1], tuv[3 * i + 2], prim, node, v);
+    R.Result.HitPoint[0] = v.Position.x, R.Result.HitPoint[1] = v.Position.y, R.Result.HitPoint[2] = v.Position.z, R.Result.HitPoint[3] = 1.0f;
+    R.Result.Normal[0] = v.Normal.x, R.Result.Normal[1] = v.Normal.y, R.Result.Normal[2] = v.Normal.z, R.Result.Normal[3] = 0.0f;
+    R.Result.Hitted = 1;
+    R.Result.T = length3(v.Position - ro);
+    R.Result.InstanceId = SS.nodes[node].instanceId;
+    R.Result.MaterialId = v.MaterialIndex;
 }
 
 static GkStatus selectDevice(Context& c)
@@ -389,6 +422,39 @@ GkStatus gk_raycast(GkContext* ctx, const float* origin_dir, uint32_t count, GkR
     return s;
 }
 
+GkStatus gk_raycast_task(GkContext* ctx, GkRayCastIO* io, uint32_t count)
+{
+    GK_CHECK_CTX(ctx);
+    if (count == 0) return GK_OK;
+    if (!io) {
+        setLastError("gk_raycast_task: null argument");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    if (!c.haveScene || !c.haveInstances) {
+        setLastError("gk_raycast_task: scene and instances must be set first");
+        return GK_ERR_NOT_READY;
+    }
+    DevBuf<GkRayCastIO> dio;
+    DevBuf<float4> dr;
+    DevBuf<float> dt;
+    DevBuf<uint32_t> di;
+    GK_CUDA(dio.reserve(count));
+    GK_CUDA(dr.reserve(2 * (size_t)count));
+    GK_CUDA(dt.reserve(3 * (size_t)count));
+    GK_CUDA(di.reserve(2 * (size_t)count));
+    GK_CUDA(cudaMemcpyAsync(dio.p, io, sizeof(GkRayCastIO) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+    k_task_pack<<<(count + 255) / 256, 256, 0, c.stream>>>(dio.p, count, dr.p);
+    GkStatus s = intersectDevice(c, dr.p, count, dt.p, di.p, false);
+    if (s != GK_OK) return s;
+    ShadeScene SS;
+    SS.verts = c.dGpuVerts.p, SS.indices = c.dIndices.p, SS.models = c.dModels.p, SS.materials = c.dMaterials.p, SS.nodes = c.dNodes.p, SS.inst = c.dInst.p;
+    SS.cubes = nullptr, SS.voxels = nullptr, SS.materialCount = c.materialCount;
+    k_task_results<<<(count + 255) / 256, 256, 0, c.stream>>>(dio.p, dt.p, di.p, count, SS);
+    GK_CUDA(cudaGetLastError());
+    GK_CUDA(cudaMemcpyAsync(io, dio.p, sizeof(GkRayCastIO) * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
+    return checkTraversalOverflow(c);
+}
+
 size_t gk_plane_bytes(const GkContext* ctx, GkPlane plane)
 {
     if (!ctx || plane < 0 || plane >= GK_PLANE_COUNT) return 0;
@@ -524,6 +590,15 @@ GkStatus gk_frame_shard_accumulate(GkContext* ctx)
 {
     GK_CHECK_CTX(ctx);
     return frameShardAccumulate(c);
+}
+
+GkStatus gk_exchange_close_peers(GkContext* ctx)
+{
+    GK_CHECK_CTX(ctx);
+    GK_CUDA(cudaStreamSynchronize(c.stream));
+    exchangeClosePeers(c);
+    frameShardClosePeers(c);
+    return GK_OK;
 }
 
 GkStatus gk_exchange_push(GkContext* ctx)

@@ -297,6 +297,7 @@ GkStatus frameShardOpen(Context& c, const void* handlesAll, uint32_t world);
 GkStatus frameShardPush(Context& c);
 GkStatus frameShardAccumulate(Context& c);
 void frameShardRelease(Context& c);
+void frameShardClosePeers(Context& c);
 GkStatus composeOwnedRows(Context& c); // gk_filters.cu: k_denoise_jbf on the owned rows + history hand-over
 GkStatus filterFrameOwnedRows(Context& c);
 void exchangeClosePeers(Context& c);

@@ -175,13 +175,18 @@ __global__ void __launch_bounds__(256) k_shard_accumulate(ShardAccArgs A)
 
 static uint32_t shardRowsPadded(const Context& c) { return ((c.height + c.tileRows * c.tileCount - 1) / (c.tileRows * c.tileCount)) * c.tileRows; }
 
-void frameShardRelease(Context& c)
+void frameShardClosePeers(Context& c)
 {
     if (c.shardOpen)
         for (uint32_t r = 0; r < c.tileCount && r < (uint32_t)kMaxPeers; ++r)
             if (r != c.tileIndex && c.shardPeer[r]) cudaIpcCloseMemHandle(c.shardPeer[r]);
     for (int r = 0; r < kMaxPeers; ++r) c.shardPeer[r] = nullptr;
     c.shardOpen = false;
+}
+
+void frameShardRelease(Context& c)
+{
+    frameShardClosePeers(c);
     if (c.shardGather) cudaFree(c.shardGather);
     c.shardGather = nullptr;
 }

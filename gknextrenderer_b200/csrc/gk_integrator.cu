@@ -1096,7 +1096,7 @@ static GkStatus traceFrameStreamed(Context& c)
         }
         const int cur = (int)(wave & 1u), nxt = cur ^ 1;
         const uint32_t sizeE = wave == 0 ? n : bound, sizeS = wave == 0 ? 0u : bound;
-        if (wave > 0 && bound <= c.streamTailPaths && c.captureWave < 0 && !c.travStats) {
+        if (wave > 0 && bound <= std::min(c.streamTailPaths, n / 8u) && c.captureWave < 0 && !c.travStats) {
             // a handful of long paths is left (dielectric primaries run to MaxNumberOfBounces): one launch walks each of them to
             // its end (trace -> shade -> trace ..., one path per lane) instead of a dozen waves of a few rays at ~65 us each
             const size_t ta = mark();
@@ -1125,7 +1125,7 @@ static GkStatus traceFrameStreamed(Context& c)
         const bool fork = sizeS && c.concurrentShadow;
         // waves below the threshold: the eight-lanes-per-ray kernel (a lone ray finishes ~4x sooner than on one lane); `bound` is
         // the size of an earlier wave, so a wave is only classed small when it certainly is
-        const bool small = wave > 0 && bound < c.coopThreshold;
+        const bool small = wave > 0 && bound < std::min(c.coopThreshold, n / 4u); // relative too: a rank of an 8-GPU frame has 0.26 M paths in all
         size_t b, d, s0 = 0, s1 = 0;
         if (fork) {
             GK_CUDA(cudaEventRecord(c.evFork, st));

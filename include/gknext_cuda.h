@@ -164,6 +164,14 @@ GkStatus gk_filter_frame(GkContext* ctx);  /* ReProject x3 + DenoiseJBF + histor
  * (src/Runtime/Engine.cpp:647-653; CPUAccelerationStructure.cpp:283-307), batched as in
  * Task.RayCast.comp.slang.  origin_dir: 6 floats per ray. */
 GkStatus gk_raycast(GkContext* ctx, const float* origin_dir, uint32_t count, GkRayCastResult* out);
+/* Replaces the GPU ray-cast task: NextEngine::RayCastGPU queues requests (src/Runtime/Engine.cpp:647-653), RayCastBuffer holds
+ * them as RayCastIO records (src/Assets/UniformBuffer.hpp:81-114) and Task.RayCast.comp.slang:31-55 answers them in place, one
+ * thread per record: FHardwareRayTracer::TraceRay(Origin, Direction, 10000) (Shading.slang:708-750: tmin EPS = 1e-3), then
+ * HitPoint = Origin + Direction * t (w = 1), Normal = the INTERPOLATED shading normal taken to world space (w = 0),
+ * T = |HitPoint - Origin|, InstanceId = the node's instance id, MaterialId = the node's material for the triangle's slot,
+ * Hitted = 1; a miss only sets Hitted = 0 and leaves the other result fields as they were.  (gk_raycast above is the CPU
+ * variant RayCastInCPU: tmax 2000, face normal, no material.)  `io` is a host array updated in place. */
+GkStatus gk_raycast_task(GkContext* ctx, GkRayCastIO* io, uint32_t count);
 /* Closest-hit queries on arbitrary rays: 8 floats per ray {O.xyz, tmin, D.xyz, tmax};
  * out_tuv 3 floats, out_ids {triangle, node-proxy index} per ray.  Host pointers. */
 GkStatus gk_intersect(GkContext* ctx, const float* rays, uint32_t count, float* out_tuv, uint32_t* out_ids);
@@ -204,6 +212,10 @@ GkStatus gk_exchange_unpack(GkContext* ctx, const void* d_all);
 GkStatus gk_exchange_ipc_handles(GkContext* ctx, void* out, size_t bytes);
 GkStatus gk_exchange_open_peers(GkContext* ctx, const void* handles_all, uint32_t world);
 GkStatus gk_exchange_push(GkContext* ctx);
+/* Unmaps the peers' planes and gather buffers (CUDA IPC).  Memory that another process has mapped must not be freed under
+ * it: before gk_resize / gk_destroy of a context whose planes were exported, EVERY rank calls this and the caller
+ * synchronises the ranks (compositor.release does both); afterwards the peer exchange has to be set up again. */
+GkStatus gk_exchange_close_peers(GkContext* ctx);
 /* Progressive rendering without the denoiser (the state gkNextBenchmark runs in, gkNextBenchmark.cpp:16-31)
  * filters every pixel on its own, so a tile-partitioned frame needs no exchange before the filters:
  *   gk_filter_frame_owned     runs the accumulate + compose passes on the rows this context owns

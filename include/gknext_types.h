@@ -204,6 +204,13 @@ typedef struct GkRayCastIn {
     float Reversed1;
 } GkRayCastIn;
 
+/* In-place record of the GPU ray-cast task: RayCastContext in assets/shaders/Task.RayCast.comp.slang, RayCastIO on the host
+ * (src/Assets/UniformBuffer.hpp:81-85). */
+typedef struct GkRayCastIO {
+    GkRayCastIn Context;
+    GkRayCastResult Result;
+} GkRayCastIO;
+
 /* One Assets::Model as it exists between Scene::Reload and Model::FreeMemory
  * (src/Assets/Scene.cpp:101-196): the backend copies during upload. */
 typedef struct GkModelDesc {
@@ -241,6 +248,7 @@ static_assert(sizeof(GkVertex) == 52, "Vertex");
 static_assert(sizeof(GkGPUVertex) == 24, "GPUVertex");
 static_assert(sizeof(GkRayCastResult) == 48, "RayCastResult");
 static_assert(sizeof(GkRayCastIn) == 48, "RayCastIn");
+static_assert(sizeof(GkRayCastIO) == 96, "RayCastIO");
 #endif
 
 #endif /* GKNEXT_TYPES_H_ */

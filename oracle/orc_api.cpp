@@ -121,6 +121,8 @@ void orc_raycast(void* h, const float* origin_dir /* 6 floats per ray */, uint32
     }
 }
 
+void orc_raycast_task(void* h, GkRayCastIO* io, uint32_t n) { rayCastTask(*(const Scene*)h, io, n); }
+
 uint32_t orc_blas_node_count(void* h, uint32_t m) { return (uint32_t)((Scene*)h)->blas[m].bvh.nodes.size(); }
 void orc_blas_nodes(void* h, uint32_t m, float* out8) { memcpy(out8, ((Scene*)h)->blas[m].bvh.nodes.data(), ((Scene*)h)->blas[m].bvh.nodes.size() * 32); }
 uint32_t orc_tlas_node_count(void* h) { return (uint32_t)((Scene*)h)->tlas.bvh.nodes.size(); }

@@ -547,4 +547,28 @@ void renderFrame(const Scene& S, const GkUniformBufferObject& U, uint32_t W, uin
     });
 }
 
+// Task.RayCast.comp.slang:31-55 — the GPU ray-cast task, one in-place RayCastIO record per ray:
+// FHardwareRayTracer::TraceRay(Origin, Direction, 10000) (Shading.slang:708-750, tmin = EPS), HitPoint = Origin + Direction * t,
+// interpolated world-space normal, T = |HitPoint - Origin|, InstanceId = node instance id, MaterialId = the node's material of
+// the triangle's slot; a miss only clears Hitted.
+void rayCastTask(const Scene& S, GkRayCastIO* io, uint32_t n)
+{
+    GkUniformBufferObject U{};
+    Ctx c{S, U, nullptr, nullptr, 0};
+    for (uint32_t i = 0; i < n; ++i) {
+        GkRayCastIO& R = io[i];
+        const f3 ro(R.Context.Origin[0], R.Context.Origin[1], R.Context.Origin[2]), rd(R.Context.Direction[0], R.Context.Direction[1], R.Context.Direction[2]);
+        Vtx v;
+        uint32_t node = 0;
+        if (traceRay(c, ro, rd, 10000.0f, v, node)) {
+            R.Result.HitPoint[0] = v.Position.x, R.Result.HitPoint[1] = v.Position.y, R.Result.HitPoint[2] = v.Position.z, R.Result.HitPoint[3] = 1.0f;
+            R.Result.Normal[0] = v.Normal.x, R.Result.Normal[1] = v.Normal.y, R.Result.Normal[2] = v.Normal.z, R.Result.Normal[3] = 0.0f;
+            R.Result.Hitted = 1;
+            R.Result.T = length(v.Position - ro);
+            R.Result.InstanceId = S.nodes[node].instanceId;
+            R.Result.MaterialId = v.MaterialIndex;
+        } else R.Result.Hitted = 0;
+    }
+}
+
 } // namespace orc

@@ -36,4 +36,7 @@ struct PtOutputs {
 void renderFrame(const Scene& S, const GkUniformBufferObject& ubo, uint32_t W, uint32_t H, const GkAmbientCube* cubes,
                  const GkVoxelData* voxels, PtOutputs& out, int threads);
 
+// the GPU ray-cast task (Task.RayCast.comp.slang:31-55) on in-place records
+void rayCastTask(const Scene& S, GkRayCastIO* io, uint32_t n);
+
 } // namespace orc

@@ -34,6 +34,7 @@ def load_oracle():
     lib.orc_intersect_bruteforce.argtypes = [_P, _P, C.c_uint32, _P, _P]
     lib.orc_intersect_bruteforce_mt.argtypes = [_P, _P, C.c_uint32, _P, _P, C.c_int]
     lib.orc_raycast.argtypes = [_P, _P, C.c_uint32, _P]
+    lib.orc_raycast_task.argtypes = [_P, _P, C.c_uint32]
     lib.orc_blas_node_count.restype = C.c_uint32
     lib.orc_blas_node_count.argtypes = [_P, C.c_uint32]
     lib.orc_blas_nodes.argtypes = [_P, C.c_uint32, _P]
@@ -130,6 +131,12 @@ class OracleScene:
         out = (GkRayCastResult * od.shape[0])()
         self.lib.orc_raycast(self.h, ptr(od), od.shape[0], out)
         return out
+
+    def raycast_task(self, io: np.ndarray):
+        """Task.RayCast.comp.slang on an (n, 24) 4-byte view of RayCastIO records, in place."""
+        assert io.dtype.itemsize == 4 and io.shape[1] == 24 and io.flags["C_CONTIGUOUS"]
+        self.lib.orc_raycast_task(self.h, io.ctypes.data_as(C.c_void_p), io.shape[0])
+        return io
 
     def render(self, ubo, width, height, threads=8, cubes=None, voxels=None):
         px = width * height

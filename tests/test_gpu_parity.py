@@ -186,6 +186,28 @@ def test_raycast_matches_raycastincpu(built):
         assert np.array_equal(_bits(np.float32(a[i].HitPoint[:] + a[i].Normal[:] + [a[i].T])), _bits(np.float32(b[i].HitPoint[:] + b[i].Normal[:] + [b[i].T])))
 
 
+def test_raycast_task_matches_task_raycast_shader(built):
+    """gk_raycast_task: the in-place RayCastIO records of Task.RayCast.comp.slang (tmin EPS, tmax 10000, interpolated normal,
+    material id, instance id); misses leave the result fields untouched except Hitted."""
+    rng = np.random.default_rng(17)
+    for scene, args, lo, hi in (("cornell", (), (-2.5, 0.2, -2.5), (2.5, 5.0, 2.5)), ("room", (60000, 5), (-9.5, 0.1, -9.5), (9.5, 3.9, 9.5))):
+        eng, r, orc, _ = _setup(scene, 64, 64, args)
+        n = 20000
+        io = np.zeros((n, 24), np.float32)
+        io[:, 0:3] = rng.uniform(lo, hi, (n, 3))
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        io[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+        io[::50, 1] = 1e6  # far above the scene, pointing anywhere: misses
+        io[:, 12:24] = 7.0  # stale result bytes: a miss must keep them
+        a, b = io.copy(), io.copy()
+        r.raycast_task(a)
+        orc.raycast_task(b)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{scene}: raycast task records differ"
+        hit = a.view(np.uint32)[:, 23] == 1
+        assert hit.any() and (~hit).any()
+        assert (a[~hit, 12:22] == 7.0).all()
+
+
 OUTLIER_FRACTION = 5e-4  # pixels whose path took a different discrete branch (ulp-level sin/cos differences)
 
 
