@@ -176,6 +176,17 @@ class Renderer:
         assert cubes.shape[1] == 14 and voxels.shape[1] == 4 and cubes.shape[0] == voxels.shape[0]
         self._check(self.lib.gk_set_probes(self.h, cubes.ctypes.data_as(C.c_void_p), voxels.ctypes.data_as(C.c_void_p), cubes.shape[0]))
 
+    def bake_probes(self, first: int, count: int):
+        """Probe baker (Bake.HwAmbientCube / FGpuProbeGenerator::Render) on probes [first, first + count)."""
+        self._check(self.lib.gk_bake_probes(self.h, first, count))
+
+    def get_probes(self):
+        """(cubes (N, 14) uint32, voxels (N, 4) uint32) of the 192 x 48 x 192 grid."""
+        n = 192 * 192 * 48
+        cubes, voxels = np.empty((n, 14), np.uint32), np.empty((n, 4), np.uint32)
+        self._check(self.lib.gk_get_probes(self.h, cubes.ctypes.data_as(C.c_void_p), voxels.ctypes.data_as(C.c_void_p), n))
+        return cubes, voxels
+
     def set_ubo(self, ubo):
         self._check(self.lib.gk_set_ubo(self.h, C.byref(ubo)))
 

@@ -151,6 +151,8 @@ CUDA_API = {
     "gk_update_materials": (C.c_int, [_P, C.POINTER(GkMaterial), C.c_uint32]),
     "gk_update_instances": (C.c_int, [_P, C.POINTER(GkNodeProxy), C.c_uint32, C.c_int]),
     "gk_set_probes": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "gk_bake_probes": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "gk_get_probes": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "gk_set_ubo": (C.c_int, [_P, C.POINTER(GkUniformBufferObject)]),
     "gk_render_frame": (C.c_int, [_P]),
     "gk_trace_frame": (C.c_int, [_P]),

@@ -10,7 +10,7 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 NVFLAGS="-O3 -std=c++17 -lineinfo -fmad=false $ARCH -Xcompiler -fPIC -Xcompiler -fno-strict-aliasing ${GK_NVCC_EXTRA:-}"
 objs=()
 pids=()
-for f in gk_api gk_scene gk_bvh_build gk_integrator gk_filters gk_exchange; do
+for f in gk_api gk_scene gk_bvh_build gk_integrator gk_filters gk_exchange gk_probes; do
   src=csrc/$f.cu; obj=build/$f.o
   objs+=("$obj")
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ -n "$(find csrc ../include -newer "$obj" \( -name '*.cuh' -o -name '*.h' \) -print -quit)" ]; then

@@ -236,7 +236,7 @@ void gk_destroy(GkContext* ctx)
     freeFrameResources(c);
     c.blasTree.release(), c.tlasTree.release();
     c.dModels.release(), c.dGpuVerts.release(), c.dIndices.release(), c.dMaterials.release(), c.dLights.release(), c.dFaceNormals.release();
-    c.dNodes.release(), c.dCubes.release(), c.dVoxels.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dBlasSrc.release(), c.dTlasSrc.release(), c.dInst.release();
+    c.dNodes.release(), c.dCubes.release(), c.dVoxels.release(), c.dCubesPrev.release(), c.dVoxelsPrev.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dBlasSrc.release(), c.dTlasSrc.release(), c.dInst.release();
     c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release(), c.dRootRef.release();
     for (int k = 0; k < 2; ++k) c.dPlocRef[k].release(), c.dPlocLo[k].release(), c.dPlocHi[k].release();
     c.dPlocNn.release(), c.dPlocValid.release(), c.dPlocPos.release();
@@ -315,6 +315,18 @@ GkStatus gk_set_probes(GkContext* ctx, const GkAmbientCube* cubes, const GkVoxel
     GK_CUDA(cudaStreamSynchronize(c.stream));
     c.haveProbes = true;
     return GK_OK;
+}
+
+GkStatus gk_bake_probes(GkContext* ctx, uint32_t first_probe, uint32_t count)
+{
+    GK_CHECK_CTX(ctx);
+    return bakeProbes(c, first_probe, count);
+}
+
+GkStatus gk_get_probes(GkContext* ctx, GkAmbientCube* cubes, GkVoxelData* voxels, size_t count)
+{
+    GK_CHECK_CTX(ctx);
+    return getProbes(c, cubes, voxels, count);
 }
 
 GkStatus gk_set_ubo(GkContext* ctx, const GkUniformBufferObject* ubo)

@@ -164,6 +164,8 @@ struct Context {
     uint32_t nodeCount = 0;
     DevBuf<GkAmbientCube> dCubes;
     DevBuf<GkVoxelData> dVoxels;
+    DevBuf<GkAmbientCube> dCubesPrev; // probe state before a gk_bake_probes call (what its gathers read)
+    DevBuf<GkVoxelData> dVoxelsPrev;
     bool haveProbes = false;
     uint64_t totalTris = 0, instancedTris = 0;
 
@@ -280,6 +282,9 @@ GkStatus traceFrame(Context& c);
 GkStatus intersectDevice(Context& c, const float4* rays, uint32_t n, float* tuv, uint32_t* ids, bool anyHit);
 GkStatus checkTraversalOverflow(Context& c); // synchronises; GK_ERR_UNSUPPORTED if a traversal dropped a stack entry
 GkStatus raycastBatch(Context& c, const float* originDir, uint32_t n, GkRayCastResult* out);
+// gk_probes.cu
+GkStatus bakeProbes(Context& c, uint32_t first, uint32_t count);
+GkStatus getProbes(Context& c, GkAmbientCube* cubes, GkVoxelData* voxels, size_t count);
 // gk_filters.cu
 GkStatus filterFrame(Context& c);
 void applyPendingHistorySwap(Context& c);

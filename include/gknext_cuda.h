@@ -148,6 +148,16 @@ GkStatus gk_update_instances(GkContext* ctx, const GkNodeProxy* nodes, uint32_t 
  * NULL (the default) means un-baked probes, i.e. all zero. */
 GkStatus gk_set_probes(GkContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels, size_t count);
 
+/* Replaces the probe-bake dispatch of RayTraceBaseRenderer::PostRender (RayTraceBaseRenderer.cpp:244-291: every frame a slice
+ * of groupPerFrame x 64 probes starting at offsetInCubes) with Bake.HwAmbientCube.comp.slang:29-46 /
+ * FGpuProbeGenerator::Render (common/AmbientCube.slang:574-629): classifies probes [first_probe, first_probe + count) of the
+ * 192 x 48 x 192 grid against the scene (six axis rays, eight diagonal rays) and gathers direct / bounced light into the
+ * faces of those near a surface (6 x (16 rays + light segment + sun ray)), blending with weight 1/8 into the stored RGB10A2
+ * values.  Works on the probe buffers of gk_set_probes (all zero when none were uploaded); uses the UBO of gk_set_ubo (sky,
+ * sun, LightCount).  Gathers read the probe state as it was before the call.  gk_get_probes copies the grid back. */
+GkStatus gk_bake_probes(GkContext* ctx, uint32_t first_probe, uint32_t count);
+GkStatus gk_get_probes(GkContext* ctx, GkAmbientCube* cubes, GkVoxelData* voxels, size_t count);
+
 /* Replaces UniformBuffer::SetValue for the frame (VulkanBaseRenderer.cpp:1370-1374). */
 GkStatus gk_set_ubo(GkContext* ctx, const GkUniformBufferObject* ubo);
 

@@ -121,6 +121,11 @@ void orc_raycast(void* h, const float* origin_dir /* 6 floats per ray */, uint32
     }
 }
 
+void orc_bake_probes(void* h, const GkUniformBufferObject* ubo, GkAmbientCube* cubes, GkVoxelData* voxels, uint32_t first, uint32_t count, int threads)
+{
+    bakeProbes(*(const Scene*)h, *ubo, cubes, voxels, first, count, threads);
+}
+
 void orc_raycast_task(void* h, GkRayCastIO* io, uint32_t n) { rayCastTask(*(const Scene*)h, io, n); }
 
 uint32_t orc_blas_node_count(void* h, uint32_t m) { return (uint32_t)((Scene*)h)->blas[m].bvh.nodes.size(); }

@@ -547,6 +547,265 @@ void renderFrame(const Scene& S, const GkUniformBufferObject& U, uint32_t W, uin
     });
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Probe baker: Bake.HwAmbientCube.comp.slang:29-46 + FGpuProbeGenerator (common/AmbientCube.slang:453-675), restated.
+// Same stated deviations as the path tracer (no textures, constant sky instead of the SH sky of SampleIBLRough), and the
+// gathers read the probe state as it was before the call (the shader's read-while-write order is undefined).
+namespace {
+
+struct c4 {
+    float x, y, z, w;
+    c4() : x(0), y(0), z(0), w(0) {}
+    c4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
+};
+inline c4 operator+(c4 a, c4 b) { return c4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+inline c4 operator*(c4 a, c4 b) { return c4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+inline c4 operator*(c4 a, float t) { return c4(a.x * t, a.y * t, a.z * t, a.w * t); }
+inline c4 operator/(c4 a, float t) { return c4(a.x / t, a.y / t, a.z / t, a.w / t); }
+inline float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; } // lerp as FMix: x(1-a) + ya
+
+inline c4 unpackRGB10A2(uint32_t p) // AmbientCube.slang:71-78 (MAX_ILLUMINANCE 512)
+{
+    return c4(float(p & 0x3FF) / 1023.0f, float((p >> 10) & 0x3FF) / 1023.0f, float((p >> 20) & 0x3FF) / 1023.0f, 0.0f) * 512.f;
+}
+inline uint32_t packRGB10A2(c4 c) // AmbientCube.slang:59-69
+{
+    float r = clampf(c.x / 512.f, 0.f, 1.f), g = clampf(c.y / 512.f, 0.f, 1.f), b = clampf(c.z / 512.f, 0.f, 1.f), a = clampf(c.w / 512.f, 0.f, 1.f);
+    return (uint32_t)(r * 1023.0f) | ((uint32_t)(g * 1023.0f) << 10) | ((uint32_t)(b * 1023.0f) << 20) | ((uint32_t)(a * 3.0f) << 30);
+}
+inline uint32_t lerpPackedColorAlt(uint32_t c0, c4 c1, float t) // AmbientCube.slang:119-126
+{
+    c4 a = unpackRGB10A2(c0);
+    return packRGB10A2(c4(mixf(a.x, c1.x, t), mixf(a.y, c1.y, t), mixf(a.z, c1.z, t), mixf(a.w, c1.w, t)));
+}
+c4 sampleCubeDI(const GkAmbientCube& cb, f3 n) // sampleAmbientCubeHL2_DI, AmbientCube.slang:128-151
+{
+    float wx = fmaxf_(n.x, 0.f), wnx = fmaxf_(-n.x, 0.f), wy = fmaxf_(n.y, 0.f), wny = fmaxf_(-n.y, 0.f), wz = fmaxf_(n.z, 0.f), wnz = fmaxf_(-n.z, 0.f);
+    float sum = wx + wnx + wy + wny + wz + wnz;
+    c4 col;
+    col = col + unpackRGB10A2(cb.PosX_D) * wx;
+    col = col + unpackRGB10A2(cb.NegX_D) * wnx;
+    col = col + unpackRGB10A2(cb.PosY_D) * wy;
+    col = col + unpackRGB10A2(cb.NegY_D) * wny;
+    col = col + unpackRGB10A2(cb.PosZ_D) * wz;
+    col = col + unpackRGB10A2(cb.NegZ_D) * wnz;
+    return col * ((sum > 0.0f) ? (1.0f / sum) : 1.0f);
+}
+c4 interpolateDI(const GkAmbientCube* cubes, const GkVoxelData* voxels, f3 pos, f3 normal) // AmbientCube.slang:275-364, T = DIAmbientCubeSampler
+{
+    const f3 off = f3(-float(GK_CUBE_SIZE_XY / 2), -1.375f, -float(GK_CUBE_SIZE_XY / 2)) * GK_CUBE_UNIT;
+    f3 np = (pos - off) / GK_CUBE_UNIT;
+    if (np.x < 0 || np.y < 0 || np.z < 0 || np.x > GK_CUBE_SIZE_XY - 1 || np.y > GK_CUBE_SIZE_Z - 1 || np.z > GK_CUBE_SIZE_XY - 1) return c4(0, 0, 0, 1);
+    int bx = (int)floorf(np.x), by = (int)floorf(np.y), bz = (int)floorf(np.z);
+    f3 fr(np.x - floorf(np.x), np.y - floorf(np.y), np.z - floorf(np.z));
+    float total = 0;
+    c4 result;
+    for (int i = 0; i < 8; ++i) {
+        int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
+        int idx = (by + oy) * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY + (bz + oz) * GK_CUBE_SIZE_XY + (bx + ox);
+        const GkVoxelData& vx = voxels[idx];
+        uint32_t p0 = vx.distanceToSolid_gg_z01, p1 = vx.distanceToSolid_x01_y01;
+        if (float((p0 >> 8) & 0xFF) / 255.0f < 0.01f) continue;
+        float dPZ = float((p0 >> 16) & 0xFF) / 255.0f, dNZ = float((p0 >> 24) & 0xFF) / 255.0f;
+        float dPX = float(p1 & 0xFF) / 255.0f, dNX = float((p1 >> 8) & 0xFF) / 255.0f, dPY = float((p1 >> 16) & 0xFF) / 255.0f, dNY = float((p1 >> 24) & 0xFF) / 255.0f;
+        f3 ptl = fr - f3((float)ox, (float)oy, (float)oz);
+        float dist = length(ptl);
+        f3 dir = normalize(ptl);
+        float hitLen = sqrtf(fmaxf_(dir.x, 0.f)) * dPX + sqrtf(fmaxf_(-dir.x, 0.f)) * dNX + sqrtf(fmaxf_(dir.y, 0.f)) * dPY + sqrtf(fmaxf_(-dir.y, 0.f)) * dNY +
+                       sqrtf(fmaxf_(dir.z, 0.f)) * dPZ + sqrtf(fmaxf_(-dir.z, 0.f)) * dNZ;
+        if (dist > hitLen + 0.05f) continue;
+        float wx = ox == 0 ? (1.0f - fr.x) : fr.x, wy = oy == 0 ? (1.0f - fr.y) : fr.y, wz = oz == 0 ? (1.0f - fr.z) : fr.z;
+        float w = wx * wy * wz;
+        result = result + sampleCubeDI(cubes[idx], normal) * w;
+        total += w;
+    }
+    return total > 0.0f ? result / total : c4(0, 0, 0, 0);
+}
+
+// FHardwareRayTracer for the baker.  RayQuery measures t in units of the given direction; Scene::trace normalises (tinybvh),
+// so tmin / tmax are scaled by |direction| and the hit distance is scaled back.
+struct BakeTracer {
+    Ctx& c;
+    bool traceRay(f3 ro, f3 rd, float maxDistance, Vtx& out) // Shading.slang:708-750
+    {
+        const float len = length(rd);
+        Hit h;
+        if (!c.S.trace(ro, rd, kEps * len, maxDistance * len, h)) return false;
+        const GkNodeProxy& px = c.S.nodes[h.inst];
+        const Model& M = c.S.models[px.modelId / 10];
+        UnpackedV v0 = unpackVertex(M.gpuVerts[M.indices[h.prim * 3]]), v1 = unpackVertex(M.gpuVerts[M.indices[h.prim * 3 + 1]]), v2 = unpackVertex(M.gpuVerts[M.indices[h.prim * 3 + 2]]);
+        f3 n = v0.N + (v1.N - v0.N) * h.u + (v2.N - v0.N) * h.v;
+        float inv[16], T[16];
+        for (int r = 0; r < 4; ++r)
+            for (int cc = 0; cc < 4; ++cc) T[r * 4 + cc] = px.worldTS[cc * 4 + r];
+        for (int k = 0; k < 16; ++k) inv[k] = (k % 5 == 0) ? 1.f : 0.f;
+        invert4x4RowMajor(T, inv);
+        f3 nw(inv[0] * n.x + inv[4] * n.y + inv[8] * n.z, inv[1] * n.x + inv[5] * n.y + inv[9] * n.z, inv[2] * n.x + inv[6] * n.y + inv[10] * n.z);
+        out.Normal = normalize(nw);
+        out.Position = ro + rd * (h.t / len);
+        out.MaterialIndex = px.matId[v0.mat & 15];
+        return true;
+    }
+    bool traceOcclusion(f3 ro, f3 rd) // :661-681
+    {
+        const float len = length(rd);
+        return c.S.anyHit(ro, rd, kEps * len, kMaxTrace * len);
+    }
+    bool traceSegment(f3 ro, f3 target, float epsilon) // :683-706
+    {
+        f3 dir = target - ro;
+        float len = length(dir);
+        f3 d = dir / len;
+        float dl = length(d);
+        return c.S.anyHit(ro, d, epsilon * dl, (len - epsilon) * dl);
+    }
+};
+
+const f2 kGrid3x3[9] = {f2(-0.667f, -0.667f), f2(0.0f, -0.667f), f2(0.667f, -0.667f), f2(-0.667f, 0.0f), f2(0.0f, 0.0f), f2(0.667f, 0.0f), f2(-0.667f, 0.667f), f2(0.0f, 0.667f), f2(0.667f, 0.667f)};
+const f2 kGrid4x4[16] = {f2(-0.75f, -0.75f), f2(-0.25f, -0.75f), f2(0.25f, -0.75f), f2(0.75f, -0.75f), f2(-0.75f, -0.25f), f2(-0.25f, -0.25f), f2(0.25f, -0.25f), f2(0.75f, -0.25f),
+                         f2(-0.75f, 0.25f),  f2(-0.25f, 0.25f),  f2(0.25f, 0.25f),  f2(0.75f, 0.25f),  f2(-0.75f, 0.75f),  f2(-0.25f, 0.75f),  f2(0.25f, 0.75f),  f2(0.75f, 0.75f)};
+
+// FaceTask, AmbientCube.slang:459-532
+void faceTask(BakeTracer& T, const GkAmbientCube* cubesPrev, const GkVoxelData* voxelsPrev, f3 origin, f3 basis, uint32_t iterate, uint32_t& directLight, uint32_t& indirectLight,
+              uint32_t& skyVisOut, uint32_t& sunVisOut)
+{
+    const GkUniformBufferObject& U = T.c.U;
+    const Scene& S = T.c.S;
+    origin = origin + basis * GK_CUBE_UNIT * 0.25f;
+    c4 directColor, bounceColor;
+    float skyVisibility = 0.0f;
+    const f2 jit = kGrid3x3[iterate % 9];
+    const float offx = jit.x * 0.25f, offy = jit.y * 0.25f;
+    for (uint32_t i = 0; i < 16; ++i) {
+        f3 hemiVec = normalize(f3(kGrid4x4[i].x + offx, kGrid4x4[i].y + offy, 1.0f));
+        f3 rayDir = alignWithNormal(hemiVec, basis);
+        Vtx hv;
+        if (T.traceRay(origin, rayDir, 20.f /* FAST_MAX_TRACE_DISTANCE */, hv)) {
+            const GkMaterial& hm = S.materials[hv.MaterialIndex];
+            c4 albedo(hm.Diffuse[0], hm.Diffuse[1], hm.Diffuse[2], hm.Diffuse[3]);
+            bounceColor = bounceColor + albedo * interpolateDI(cubesPrev, voxelsPrev, hv.Position, hv.Normal) * 1.25f;
+        } else {
+            float k = U.HasSky ? U.SkyIntensity : 0.0f;
+            directColor = directColor + c4(U.BackGroundColor[0], U.BackGroundColor[1], U.BackGroundColor[2], 1.0f) * k;
+            skyVisibility += 1.0f;
+        }
+    }
+    directColor = directColor / 16.0f;
+    bounceColor = bounceColor / 16.0f;
+    if (U.LightCount > 0) {
+        const GkLightObject& L = S.lights[0];
+        const GkMaterial& lm = S.materials[L.lightMatIdx];
+        c4 lightPower(lm.Diffuse[0], lm.Diffuse[1], lm.Diffuse[2], lm.Diffuse[3]);
+        f3 p1(L.p1[0], L.p1[1], L.p1[2]), p3(L.p3[0], L.p3[1], L.p3[2]);
+        f3 lightPos(mixf(p1.x, p3.x, 0.5f), mixf(p1.y, p3.y, 0.5f), mixf(p1.z, p3.z, 0.5f));
+        float lightAtten = T.traceSegment(origin, lightPos, GK_CUBE_UNIT * 0.5f) ? 0.0f : 1.0f;
+        f3 lightDir = normalize(lightPos - origin);
+        float ndotl = clampf(dot(basis, lightDir), 0.0f, 1.0f);
+        float distance = length(lightPos - origin);
+        float attenuation = ndotl * L.normal_area[3] / (distance * distance * 3.14159f);
+        directColor = directColor + lightPower * attenuation * lightAtten;
+    }
+    if (U.HasSun) {
+        f3 sunDir(U.SunDirection[0], U.SunDirection[1], U.SunDirection[2]);
+        float sunAtten = T.traceOcclusion(origin, sunDir) ? 0.0f : 1.0f;
+        float ndotl = clampf(dot(basis, sunDir), 0.0f, 1.0f);
+        sunVisOut = sunAtten > 0.0f ? 1u : 0u;
+        directColor = directColor + c4(U.SunColor[0], U.SunColor[1], U.SunColor[2], U.SunColor[3]) * sunAtten * ndotl * (U.HasSun ? 1.0f : 0.0f) * 0.25f;
+    }
+    const float currWeight = 0.125f;
+    skyVisOut = (uint32_t)mixf((float)skyVisOut, 255.0f * skyVisibility / 16.0f, currWeight);
+    directLight = lerpPackedColorAlt(directLight, directColor, currWeight);
+    indirectLight = lerpPackedColorAlt(indirectLight, bounceColor, currWeight);
+}
+
+bool insideGeometry(BakeTracer& T, f3 origin, f3 rayDir, uint32_t& outMaterialId, float& outDistanceToSolid) // AmbientCube.slang:547-571
+{
+    Vtx hv;
+    if (T.traceRay(origin, rayDir, GK_CUBE_UNIT * 64, hv)) {
+        float hitDist = length(hv.Position - origin);
+        outDistanceToSolid = hitDist;
+        if (outDistanceToSolid <= GK_CUBE_UNIT) {
+            const GkMaterial& hm = T.c.S.materials[hv.MaterialIndex];
+            outMaterialId = hv.MaterialIndex;
+            if (dot(hv.Normal, rayDir) > 0.0f || ((hm.MaterialModel == GK_MAT_DIFFUSE_LIGHT) && hitDist < 0.02f)) {
+                outDistanceToSolid = 0;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+float detectDistance(BakeTracer& T, f3 origin, f3 rayDir) // AmbientCube.slang:534-545
+{
+    Vtx hv;
+    if (T.traceRay(origin, rayDir, GK_CUBE_UNIT * 64, hv)) return length(hv.Position - origin);
+    return 255.f;
+}
+inline uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return (a & 0xFF) | ((b & 0xFF) << 8) | ((c & 0xFF) << 16) | ((d & 0xFF) << 24); }
+
+} // namespace
+
+// Bake.HwAmbientCube main + FGpuProbeGenerator::Render (AmbientCube.slang:574-629) for probes [first, first + count)
+void bakeProbes(const Scene& S, const GkUniformBufferObject& U, GkAmbientCube* cubes, GkVoxelData* voxels, uint32_t first, uint32_t count, int threads)
+{
+    const size_t total = (size_t)GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_Z;
+    std::vector<GkAmbientCube> cubesPrev(cubes, cubes + total);
+    std::vector<GkVoxelData> voxelsPrev(voxels, voxels + total);
+    auto work = [&](uint32_t lo, uint32_t hi) {
+        Ctx ctx{S, U, nullptr, nullptr, 0};
+        BakeTracer T{ctx};
+        for (uint32_t gIdx = lo; gIdx < hi; ++gIdx) {
+            const uint32_t y = gIdx / (GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY);
+            const uint32_t z = (gIdx - y * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY) / GK_CUBE_SIZE_XY;
+            const uint32_t x = gIdx - y * GK_CUBE_SIZE_XY * GK_CUBE_SIZE_XY - z * GK_CUBE_SIZE_XY;
+            const f3 cubeOffset = f3(-float(GK_CUBE_SIZE_XY / 2), -1.375f, -float(GK_CUBE_SIZE_XY / 2)) * GK_CUBE_UNIT;
+            const f3 origin = f3((float)x, (float)y, (float)z) * GK_CUBE_UNIT + cubeOffset;
+            GkVoxelData& vox = voxels[gIdx];
+            GkAmbientCube& cube = cubes[gIdx];
+            vox.matId = 0;
+            float distPY = 255.0f, distNY = 255.0f, distPX = 255.0f, distNX = 255.0f, distPZ = 255.0f, distNZ = 255.0f;
+            insideGeometry(T, origin, f3(0, 1, 0), vox.matId, distPY);
+            insideGeometry(T, origin, f3(0, -1, 0), vox.matId, distNY);
+            insideGeometry(T, origin, f3(1, 0, 0), vox.matId, distPX);
+            insideGeometry(T, origin, f3(-1, 0, 0), vox.matId, distNX);
+            insideGeometry(T, origin, f3(0, 0, 1), vox.matId, distPZ);
+            insideGeometry(T, origin, f3(0, 0, -1), vox.matId, distNZ);
+            float minDist = fminf_(fminf_(fminf_(distPY, distNY), fminf_(distPX, distNX)), fminf_(distPZ, distNZ));
+            if (minDist > 254.0f) {
+                const f3 diag[8] = {f3(1, 1, 1), f3(-1, 1, 1), f3(-1, -1, 1), f3(-1, 1, 1), f3(1, 1, -1), f3(-1, 1, -1), f3(-1, -1, -1), f3(-1, 1, -1)};
+                for (int k = 0; k < 8; ++k) minDist = fminf_(minDist, detectDistance(T, origin, diag[k]));
+            }
+            distPY = clampf(distPY * 4.0f, 0.f, 1.f), distNY = clampf(distNY * 4.0f, 0.f, 1.f), distPX = clampf(distPX * 4.0f, 0.f, 1.f);
+            distNX = clampf(distNX * 4.0f, 0.f, 1.f), distPZ = clampf(distPZ * 4.0f, 0.f, 1.f), distNZ = clampf(distNZ * 4.0f, 0.f, 1.f);
+            const float inside = distPY * distNY * distPX * distNX * distPZ * distNZ;
+            vox.distanceToSolid_gg_z01 = pack4((uint32_t)(minDist / GK_CUBE_UNIT), (uint32_t)(inside * 255.0f), (uint32_t)(distPZ * 255.0f), (uint32_t)(distNZ * 255.0f));
+            vox.distanceToSolid_x01_y01 = pack4((uint32_t)(distPX * 255.0f), (uint32_t)(distNX * 255.0f), (uint32_t)(distPY * 255.0f), (uint32_t)(distNY * 255.0f));
+            if (minDist < 4) {
+                const uint32_t iterate = vox.age;
+                vox.age = vox.age + 1;
+                uint32_t sv0[4] = {cube.skyVisibility_pznzpyny & 0xFF, (cube.skyVisibility_pznzpyny >> 8) & 0xFF, (cube.skyVisibility_pznzpyny >> 16) & 0xFF, (cube.skyVisibility_pznzpyny >> 24) & 0xFF};
+                uint32_t sv1[4] = {cube.skyVisibility_pxnxs0s1 & 0xFF, (cube.skyVisibility_pxnxs0s1 >> 8) & 0xFF, (cube.skyVisibility_pxnxs0s1 >> 16) & 0xFF, (cube.skyVisibility_pxnxs0s1 >> 24) & 0xFF};
+                uint32_t sunvis = 0;
+                faceTask(T, cubesPrev.data(), voxelsPrev.data(), origin, f3(0, 1, 0), iterate, cube.PosY_D, cube.PosY, sv0[2], sv1[2]);
+                faceTask(T, cubesPrev.data(), voxelsPrev.data(), origin, f3(0, -1, 0), iterate, cube.NegY_D, cube.NegY, sv0[3], sunvis);
+                faceTask(T, cubesPrev.data(), voxelsPrev.data(), origin, f3(1, 0, 0), iterate, cube.PosX_D, cube.PosX, sv1[0], sunvis);
+                faceTask(T, cubesPrev.data(), voxelsPrev.data(), origin, f3(-1, 0, 0), iterate, cube.NegX_D, cube.NegX, sv1[1], sunvis);
+                faceTask(T, cubesPrev.data(), voxelsPrev.data(), origin, f3(0, 0, 1), iterate, cube.PosZ_D, cube.PosZ, sv0[0], sunvis);
+                faceTask(T, cubesPrev.data(), voxelsPrev.data(), origin, f3(0, 0, -1), iterate, cube.NegZ_D, cube.NegZ, sv0[1], sunvis);
+                cube.skyVisibility_pznzpyny = pack4(sv0[0], sv0[1], sv0[2], sv0[3]);
+                cube.skyVisibility_pxnxs0s1 = pack4(sv1[0], sv1[1], sv1[2], sv1[3]);
+            }
+        }
+    };
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        const uint32_t lo = first + (uint32_t)((uint64_t)count * t / threads), hi = first + (uint32_t)((uint64_t)count * (t + 1) / threads);
+        pool.emplace_back(work, lo, hi);
+    }
+    for (auto& th : pool) th.join();
+}
+
 // Task.RayCast.comp.slang:31-55 — the GPU ray-cast task, one in-place RayCastIO record per ray:
 // FHardwareRayTracer::TraceRay(Origin, Direction, 10000) (Shading.slang:708-750, tmin = EPS), HitPoint = Origin + Direction * t,
 // interpolated world-space normal, T = |HitPoint - Origin|, InstanceId = node instance id, MaterialId = the node's material of

@@ -36,6 +36,9 @@ struct PtOutputs {
 void renderFrame(const Scene& S, const GkUniformBufferObject& ubo, uint32_t W, uint32_t H, const GkAmbientCube* cubes,
                  const GkVoxelData* voxels, PtOutputs& out, int threads);
 
+// Bake.HwAmbientCube.comp.slang:29-46 + FGpuProbeGenerator::Render (AmbientCube.slang:574-629) on probes [first, first + count)
+void bakeProbes(const Scene& S, const GkUniformBufferObject& U, GkAmbientCube* cubes, GkVoxelData* voxels, uint32_t first, uint32_t count, int threads);
+
 // the GPU ray-cast task (Task.RayCast.comp.slang:31-55) on in-place records
 void rayCastTask(const Scene& S, GkRayCastIO* io, uint32_t n);
 

@@ -35,6 +35,7 @@ def load_oracle():
     lib.orc_intersect_bruteforce_mt.argtypes = [_P, _P, C.c_uint32, _P, _P, C.c_int]
     lib.orc_raycast.argtypes = [_P, _P, C.c_uint32, _P]
     lib.orc_raycast_task.argtypes = [_P, _P, C.c_uint32]
+    lib.orc_bake_probes.argtypes = [_P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_int]
     lib.orc_blas_node_count.restype = C.c_uint32
     lib.orc_blas_node_count.argtypes = [_P, C.c_uint32]
     lib.orc_blas_nodes.argtypes = [_P, C.c_uint32, _P]
@@ -137,6 +138,11 @@ class OracleScene:
         assert io.dtype.itemsize == 4 and io.shape[1] == 24 and io.flags["C_CONTIGUOUS"]
         self.lib.orc_raycast_task(self.h, io.ctypes.data_as(C.c_void_p), io.shape[0])
         return io
+
+    def bake_probes(self, ubo, cubes: np.ndarray, voxels: np.ndarray, first: int, count: int, threads=8):
+        """Probe baker restatement, in place on cubes (N, 14) / voxels (N, 4) uint32."""
+        assert cubes.dtype == np.uint32 and voxels.dtype == np.uint32 and cubes.flags["C_CONTIGUOUS"] and voxels.flags["C_CONTIGUOUS"]
+        self.lib.orc_bake_probes(self.h, C.cast(C.byref(ubo), _P), ptr(cubes), ptr(voxels), first, count, threads)
 
     def render(self, ubo, width, height, threads=8, cubes=None, voxels=None):
         px = width * height

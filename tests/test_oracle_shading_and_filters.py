@@ -228,3 +228,33 @@ def test_pcg4d_reference_vector(built):
     eng.set(TotalFrames=8)
     c = orc.render(eng.ubo(8, 8), 8, 8, threads=1)
     assert np.array_equal(a["diffuse"], b["diffuse"]) and not np.array_equal(a["diffuse"], c["diffuse"])
+
+
+def test_probe_baker_oracle_is_deterministic_and_lights_surface_probes():
+    """Oracle restatement of FGpuProbeGenerator::Render on the Cornell box: independent of the thread count, probes next to
+    the walls get non-zero direct light (the area light through TraceSegment), probes in empty space keep zero faces."""
+    import gknextrenderer_b200 as gk
+    import oracle_lib as ol
+    eng = gk.Engine("cornell")
+    eng.set(TAA=0)
+    eng.update_nodes()
+    nodes, n = eng.update_nodes()
+    orc = ol.OracleScene(eng.scene_desc(), nodes, n)
+    ubo = eng.ubo(64, 64)
+    total = 192 * 192 * 48
+    first, count = 8 * 192 * 192 + 88 * 192, 16 * 192
+    res = []
+    for threads in (1, 4):
+        cubes, voxels = np.zeros((total, 14), np.uint32), np.zeros((total, 4), np.uint32)
+        for _ in range(2):
+            orc.bake_probes(ubo, cubes, voxels, first, count, threads=threads)
+        res.append((cubes.copy(), voxels.copy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    cubes, voxels = res[0]
+    sl = slice(first, first + count)
+    assert not voxels[:first].any() and not voxels[first + count:].any()
+    surface = voxels[sl, 1] == 2          # aged twice: within reach of a surface
+    assert 20 < surface.sum() < count
+    assert (cubes[sl][surface][:, 6:12] != 0).any()          # direct light arrived
+    assert not cubes[sl][~surface].any()                      # far probes: faces untouched
+    assert ((voxels[sl, 2] & 0xFF) > 0).any()                 # distance-to-solid byte set for open-space probes
