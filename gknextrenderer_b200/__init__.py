@@ -104,6 +104,14 @@ class Engine:
         n = self.lib.gkh_update_nodes(self.h)
         return self.lib.gkh_node_proxies(self.h), int(n)
 
+    def changed_proxies(self):
+        """Indices of the proxies the last update_nodes() rewrote, or None when it was a full pass."""
+        ptr = C.POINTER(C.c_uint32)()
+        n = self.lib.gkh_changed_proxies(self.h, C.byref(ptr))
+        if n < 0:
+            return None
+        return np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+
     def mark_dirty(self):
         self.lib.gkh_mark_dirty(self.h)
 
@@ -163,6 +171,12 @@ class Renderer:
 
     def update_instances(self, nodes, count, refit=False):
         self._check(self.lib.gk_update_instances(self.h, nodes, count, 1 if refit else 0))
+
+    def update_instances_sparse(self, indices, proxies, refit=True):
+        """gk_update_instances_sparse: `proxies[k]` replaces record `indices[k]` of the array already on the device."""
+        indices = np.ascontiguousarray(indices, np.uint32)
+        assert len(proxies) == indices.size
+        self._check(self.lib.gk_update_instances_sparse(self.h, indices.ctypes.data_as(C.c_void_p), C.cast(proxies, C.c_void_p), indices.size, 1 if refit else 0))
 
     def load(self, engine: Engine, refit=False):
         self.upload_scene(engine.scene_desc())

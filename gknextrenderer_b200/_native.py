@@ -150,6 +150,7 @@ CUDA_API = {
     "gk_upload_scene": (C.c_int, [_P, C.POINTER(GkSceneDesc)]),
     "gk_update_materials": (C.c_int, [_P, C.POINTER(GkMaterial), C.c_uint32]),
     "gk_update_instances": (C.c_int, [_P, C.POINTER(GkNodeProxy), C.c_uint32, C.c_int]),
+    "gk_update_instances_sparse": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_int]),
     "gk_set_probes": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "gk_bake_probes": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "gk_get_probes": (C.c_int, [_P, _P, _P, C.c_size_t]),
@@ -203,6 +204,7 @@ HOST_API = {
     "gkh_node_proxies": (C.POINTER(GkNodeProxy), [_P]),
     "gkh_mark_dirty": (None, [_P]),
     "gkh_scene_step": (None, [_P, C.c_uint32]),
+    "gkh_changed_proxies": (C.c_int64, [_P, C.POINTER(C.POINTER(C.c_uint32))]),
     "gkh_set_node_translation": (C.c_int, [_P, C.c_uint32, C.c_float, C.c_float, C.c_float]),
     "gkh_set_setting": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "gkh_set_camera_lookat": (C.c_int, [_P, _P, _P, _P, C.c_float]),

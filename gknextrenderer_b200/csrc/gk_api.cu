@@ -236,7 +236,7 @@ void gk_destroy(GkContext* ctx)
     freeFrameResources(c);
     c.blasTree.release(), c.tlasTree.release();
     c.dModels.release(), c.dGpuVerts.release(), c.dIndices.release(), c.dMaterials.release(), c.dLights.release(), c.dFaceNormals.release();
-    c.dNodes.release(), c.dCubes.release(), c.dVoxels.release(), c.dCubesPrev.release(), c.dVoxelsPrev.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dBlasSrc.release(), c.dTlasSrc.release(), c.dInst.release();
+    c.dNodes.release(), c.dSparseNodes.release(), c.dSparseIdx.release(), c.dCubes.release(), c.dVoxels.release(), c.dCubesPrev.release(), c.dVoxelsPrev.release(), c.dTris.release(), c.dBlasNodes.release(), c.dTlasNodes.release(), c.dBlasSrc.release(), c.dTlasSrc.release(), c.dInst.release();
     c.dTaskA.release(), c.dTaskB.release(), c.dCounters.release(), c.dSortTemp.release(), c.dGroupLo.release(), c.dGroupHi.release(), c.dGroupRoot.release(), c.dRootRef.release();
     for (int k = 0; k < 2; ++k) c.dPlocRef[k].release(), c.dPlocLo[k].release(), c.dPlocHi[k].release();
     c.dPlocNn.release(), c.dPlocValid.release(), c.dPlocPos.release();
@@ -295,6 +295,12 @@ GkStatus gk_update_instances(GkContext* ctx, const GkNodeProxy* nodes, uint32_t 
 {
     GK_CHECK_CTX(ctx);
     return updateInstances(c, nodes, count, refit != 0);
+}
+
+GkStatus gk_update_instances_sparse(GkContext* ctx, const uint32_t* indices, const GkNodeProxy* proxies, uint32_t changed, int refit)
+{
+    GK_CHECK_CTX(ctx);
+    return updateInstancesSparse(c, indices, proxies, changed, refit != 0);
 }
 
 GkStatus gk_set_probes(GkContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels, size_t count)

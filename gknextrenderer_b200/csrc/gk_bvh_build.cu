@@ -1098,6 +1098,50 @@ GkStatus buildBlasForest(Context& c)
     return GK_OK;
 }
 
+__global__ void k_scatter_proxies(const uint32_t* __restrict__ indices, const GkNodeProxy* __restrict__ src, uint32_t changed, uint32_t count, GkNodeProxy* __restrict__ nodes)
+{
+    // 208-byte records as 13 x 16 bytes: one thread per 16-byte piece
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t rec = t / 13u, piece = t - rec * 13u;
+    if (rec >= changed) return;
+    const uint32_t dst = indices[rec];
+    if (dst >= count) return;
+    reinterpret_cast<uint4*>(nodes + dst)[piece] = reinterpret_cast<const uint4*>(src + rec)[piece];
+}
+
+static GkStatus updateInstancesOnDevice(Context& c, uint32_t count, bool refit, cudaEvent_t e0, cudaEvent_t e1, const GkNodeProxy* hostNodes);
+
+// Sparse form: only `changed` node proxies travel (Scene::UpdateNodes rewrites all of them every dirty frame,
+// Scene.cpp:464-511; MagicaLego moves a handful of bricks per frame, MagicaLegoGameInstance.cpp:746-807); the rest of the
+// array stays on the device.
+GkStatus updateInstancesSparse(Context& c, const uint32_t* indices, const GkNodeProxy* proxies, uint32_t changed, bool refit)
+{
+    cudaStream_t st = c.stream;
+    if (!c.haveScene || !c.haveInstances) {
+        setLastError("gk_update_instances_sparse: a full gk_update_instances must come first");
+        return GK_ERR_NOT_READY;
+    }
+    if (changed && (!indices || !proxies)) {
+        setLastError("gk_update_instances_sparse: null argument");
+        return GK_ERR_INVALID_ARGUMENT;
+    }
+    for (uint32_t k = 0; k < changed; ++k)
+        if (indices[k] >= c.nodeCount) {
+            setLastError("gk_update_instances_sparse: proxy index beyond the uploaded array");
+            return GK_ERR_INVALID_ARGUMENT;
+        }
+    ScopedEvents evs(2);
+    cudaEventRecord(evs.e[0], st);
+    if (changed) {
+        GK_CUDA(c.dSparseIdx.reserve(changed));
+        GK_CUDA(c.dSparseNodes.reserve(changed));
+        GK_CUDA(cudaMemcpyAsync(c.dSparseIdx.p, indices, sizeof(uint32_t) * changed, cudaMemcpyHostToDevice, st));
+        GK_CUDA(cudaMemcpyAsync(c.dSparseNodes.p, proxies, sizeof(GkNodeProxy) * changed, cudaMemcpyHostToDevice, st));
+        k_scatter_proxies<<<gridFor((size_t)changed * 13, 256), 256, 0, st>>>(c.dSparseIdx.p, c.dSparseNodes.p, changed, c.nodeCount, c.dNodes.p);
+    }
+    return updateInstancesOnDevice(c, c.nodeCount, refit, evs.e[0], evs.e[1], nullptr);
+}
+
 GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, bool refit)
 {
     cudaStream_t st = c.stream;
@@ -1109,13 +1153,19 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
         setLastError("gk_update_instances: empty instance list");
         return GK_ERR_INVALID_ARGUMENT;
     }
-    Lbvh& T = c.tlasTree;
-    if (refit && (!c.haveInstances || count != T.n)) refit = false;
     ScopedEvents evs(2);
-    cudaEvent_t e0 = evs.e[0], e1 = evs.e[1];
-    cudaEventRecord(e0, st);
+    cudaEventRecord(evs.e[0], st);
     GK_CUDA(c.dNodes.reserve(count));
     GK_CUDA(cudaMemcpyAsync(c.dNodes.p, nodes, sizeof(GkNodeProxy) * count, cudaMemcpyHostToDevice, st));
+    return updateInstancesOnDevice(c, count, refit, evs.e[0], evs.e[1], nodes);
+}
+
+// Instance records, world boxes and the TLAS (refit or build) from the node proxies in c.dNodes.
+static GkStatus updateInstancesOnDevice(Context& c, uint32_t count, bool refit, cudaEvent_t e0, cudaEvent_t e1, const GkNodeProxy* nodes)
+{
+    cudaStream_t st = c.stream;
+    Lbvh& T = c.tlasTree;
+    if (refit && (!c.haveInstances || count != T.n)) refit = false;
     c.nodeCount = count;
     T.n = count;
     GK_CUDA(T.plo.reserve(count));
@@ -1172,13 +1222,15 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
     }
     cudaEventRecord(e1, st);
     GK_CUDA(cudaGetLastError());
-    // instanced triangle count (host side, from the proxies the caller handed over)
-    uint64_t inst = 0;
-    for (uint32_t i = 0; i < count; ++i) {
-        const uint32_t m = nodes[i].modelId / 10;
-        if (nodes[i].visible && !nodes[i].nort && m < c.models.size()) inst += c.models[m].triCount;
+    // instanced triangle count (host side, from the proxies the caller handed over; a sparse update keeps the last figure)
+    if (nodes) {
+        uint64_t inst = 0;
+        for (uint32_t i = 0; i < count; ++i) {
+            const uint32_t m = nodes[i].modelId / 10;
+            if (nodes[i].visible && !nodes[i].nort && m < c.models.size()) inst += c.models[m].triCount;
+        }
+        c.instancedTris = inst;
     }
-    c.instancedTris = inst;
     GK_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);

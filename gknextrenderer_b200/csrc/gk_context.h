@@ -161,6 +161,8 @@ struct Context {
     DevBuf<GkLightObject> dLights;
     DevBuf<float4> dFaceNormals; // per triangle (model order): FCPUBLASVertInfo::normal
     DevBuf<GkNodeProxy> dNodes;
+    DevBuf<GkNodeProxy> dSparseNodes; // staging of gk_update_instances_sparse
+    DevBuf<uint32_t> dSparseIdx;
     uint32_t nodeCount = 0;
     DevBuf<GkAmbientCube> dCubes;
     DevBuf<GkVoxelData> dVoxels;
@@ -275,6 +277,7 @@ GkStatus uploadScene(Context& c, const GkSceneDesc& d);
 // gk_bvh_build.cu
 GkStatus buildBlasForest(Context& c);
 GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, bool refit);
+GkStatus updateInstancesSparse(Context& c, const uint32_t* indices, const GkNodeProxy* proxies, uint32_t changed, bool refit);
 // gk_integrator.cu
 GkStatus allocFrameResources(Context& c);
 void freeFrameResources(Context& c);

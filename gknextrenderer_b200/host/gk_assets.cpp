@@ -269,6 +269,47 @@ bool Scene::UpdateNodes() // Scene.cpp:464-511
 {
     if (nodes_.empty() || !sceneDirty_) return false;
     sceneDirty_ = false;
+    if (!fullDirty_ && proxyOffset_.size() == nodes_.size() + 1) {
+        // ---- incremental: only the marked nodes and the ones still settling (see MarkNodeDirty)
+        std::vector<uint32_t> set(touched_);
+        set.insert(set.end(), settling_.begin(), settling_.end());
+        std::sort(set.begin(), set.end());
+        set.erase(std::unique(set.begin(), set.end()), set.end());
+        touched_.clear(), settling_.clear(), changedProxies_.clear();
+        bool moved = false, structural = false;
+        auto sections = [&](uint32_t i) {
+            const auto& node = nodes_[i];
+            return (node->IsDrawable() && node->GetModel() < models_.size()) ? models_[node->GetModel()].SectionCount() : 0u;
+        };
+        for (uint32_t i : set) // a node whose proxy count changed reshapes the list: full pass below, before anything ticks
+            if (i < nodes_.size() && proxyOffset_[i + 1] - proxyOffset_[i] != sections(i)) structural = true;
+        for (uint32_t i : set) {
+            if (structural || i >= nodes_.size()) continue;
+            auto& node = nodes_[i];
+            const uint32_t want = sections(i);
+            if (!node->IsDrawable()) continue;
+            const bool unsettled = node->IsUnsettled();
+            mat4 combined;
+            if (node->TickVelocity(combined)) moved = true;
+            if (unsettled) settling_.push_back(i);
+            for (uint32_t section = 0; section < want; ++section) {
+                NodeProxy& proxy = nodeProxys_[proxyOffset_[i] + section];
+                proxy = node->GetNodeProxy();
+                memcpy(proxy.combinedPrevTS, combined.data(), 64);
+                proxy.modelId = node->GetModel() * 10 + section;
+                proxy.nort = section == 0 ? 0 : 1;
+                changedProxies_.push_back(proxyOffset_[i] + section);
+            }
+        }
+        if (!structural) {
+            lastUpdateFull_ = false;
+            if (moved) sceneDirty_ = true; // Scene.cpp:509: a moving node keeps the scene dirty for the next frame
+            return true;
+        }
+        settling_.clear();
+    }
+    fullDirty_ = false, lastUpdateFull_ = true;
+    touched_.clear(), settling_.clear(), changedProxies_.clear();
     // The proxy of a node depends on that node only, so large scenes are filled by several threads:
     // pass 1 counts the proxies of every node (drawable, valid model, one per section), pass 2 writes
     // them at their prefix offsets.  The result is identical to the sequential loop of the reference.
@@ -281,11 +322,15 @@ bool Scene::UpdateNodes() // Scene.cpp:464-511
         offset[i + 1] = offset[i] + c;
     }
     nodeProxys_.resize(offset[n]);
+    proxyOffset_ = offset;
     std::atomic<bool> moved{false};
+    std::mutex settleMutex;
     auto fill = [&](size_t lo, size_t hi) {
+        std::vector<uint32_t> unsettledHere;
         for (size_t i = lo; i < hi; ++i) {
             auto& node = nodes_[i];
             if (!node->IsDrawable()) continue;
+            if (node->IsUnsettled()) unsettledHere.push_back((uint32_t)i);
             mat4 combined;
             if (node->TickVelocity(combined)) moved.store(true, std::memory_order_relaxed);
             if (node->GetModel() >= models_.size()) continue;
@@ -298,6 +343,10 @@ bool Scene::UpdateNodes() // Scene.cpp:464-511
                 proxy.nort = section == 0 ? 0 : 1;
             }
         }
+        if (!unsettledHere.empty()) {
+            std::lock_guard<std::mutex> lock(settleMutex);
+            settling_.insert(settling_.end(), unsettledHere.begin(), unsettledHere.end());
+        }
     };
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned threads = n < 16384 ? 1u : std::min(8u, hw);
@@ -307,7 +356,7 @@ bool Scene::UpdateNodes() // Scene.cpp:464-511
         for (unsigned t = 0; t < threads; ++t) pool.emplace_back(fill, n * t / threads, n * (t + 1) / threads);
         for (auto& th : pool) th.join();
     }
-    if (moved.load()) MarkDirty();
+    if (moved.load()) sceneDirty_ = true; // Scene.cpp:509 (the next pass only has to settle the nodes that moved)
     return true;
 }
 
@@ -554,8 +603,8 @@ void BrickFieldStep(Scene& scene, uint32_t frame, uint32_t seed)
         const int gx = (int)(U(rng) * G) - G / 2, gz = (int)(U(rng) * G) - G / 2, gy = (int)(U(rng) * U(rng) * 24.f);
         nodes[i]->SetTranslation(vec3(gx * 0.08f, gy * 0.095f, gz * 0.08f));
         nodes[i]->RecalcTransform(true);
+        scene.MarkNodeDirty((uint32_t)i);
     }
-    scene.MarkDirty();
 }
 
 void InstancedCity(Scene& scene, uint32_t variants, uint32_t gridSide, uint32_t seed, int facadeN)

@@ -121,6 +121,7 @@ public:
     bool IsDrawable() const { return modelId_ != (uint32_t)-1; }
     uint32_t GetInstanceId() const { return instanceId_; }
     bool TickVelocity(mat4& combinedTS);
+    bool IsUnsettled() const { return prevTransform_ != transform_; } // the next tick changes combinedPrevTS again
     void SetMaterial(const std::vector<uint32_t>& m);
     const std::array<uint32_t, 16>& Materials() const { return materialIdx_; }
     NodeProxy GetNodeProxy() const;
@@ -167,7 +168,13 @@ public:
     // Scene::UpdateNodesGpuDriven (Scene.cpp:464-511): one proxy per (drawable node, section).
     bool UpdateNodes();
     const ProxyVector& GetNodeProxys() const { return nodeProxys_; }
-    void MarkDirty() { sceneDirty_ = true; }
+    void MarkDirty() { sceneDirty_ = true, fullDirty_ = true; }
+    // A caller that knows WHICH node it changed says so: the next UpdateNodes then re-evaluates only the marked nodes and
+    // the nodes still settling from the previous tick (their combinedPrevTS changes once more); every other proxy is what
+    // the full loop of the reference would write again.  ChangedProxies() lists the records that call rewrote.
+    void MarkNodeDirty(uint32_t node) { touched_.push_back(node), sceneDirty_ = true; }
+    bool LastUpdateWasFull() const { return lastUpdateFull_; }
+    const std::vector<uint32_t>& ChangedProxies() const { return changedProxies_; }
     std::vector<GkMaterial> GpuMaterials() const;
 
     // flat view for gk_upload_scene (pointers stay valid while the scene is unchanged)
@@ -180,7 +187,8 @@ private:
     std::vector<LightObject> lights_;
     EnvironmentSetting envSettings_;
     uint32_t cameraIdx_ = 0, selectedId_ = (uint32_t)-1;
-    bool sceneDirty_ = true;
+    bool sceneDirty_ = true, fullDirty_ = true, lastUpdateFull_ = true;
+    std::vector<uint32_t> touched_, settling_, proxyOffset_, changedProxies_;
     ProxyVector nodeProxys_;
     std::vector<GkModelDesc> modelDescs_;
     std::vector<GkMaterial> gpuMaterials_;

@@ -146,7 +146,14 @@ void CudaPathTracingRenderer::BeforeNextFrame()
         // Here an update with an unchanged instance count may refit the existing tree; the backend
         // falls back to a rebuild by itself when the refitted tree got too loose.
         const bool refit = instancesUploaded_ && px.size() == lastInstanceCount_;
-        check(gk_update_instances(ctx_, px.data(), (uint32_t)px.size(), refit ? 1 : 0), "gk_update_instances");
+        if (refit && !scene.LastUpdateWasFull() && scene.ChangedProxies().size() * 4 < px.size()) {
+            // few nodes changed (MarkNodeDirty): only their proxies travel, the rest of the array is on the device already
+            const auto& changed = scene.ChangedProxies();
+            sparseStaging_.resize(changed.size());
+            for (size_t k = 0; k < changed.size(); ++k) sparseStaging_[k] = px[changed[k]];
+            check(gk_update_instances_sparse(ctx_, changed.data(), sparseStaging_.data(), (uint32_t)changed.size(), 1), "gk_update_instances_sparse");
+        } else
+            check(gk_update_instances(ctx_, px.data(), (uint32_t)px.size(), refit ? 1 : 0), "gk_update_instances");
         updatesSinceRebuild_ = refit ? updatesSinceRebuild_ + 1 : 0;
         lastInstanceCount_ = px.size();
         instancesUploaded_ = true;

@@ -117,6 +117,7 @@ private:
     bool traceAllRows_ = false;
     bool instancesUploaded_ = false;
     size_t lastInstanceCount_ = 0;
+    std::vector<GkNodeProxy> sparseStaging_;
     uint32_t updatesSinceRebuild_ = 0;
 };
 

@@ -74,6 +74,14 @@ uint32_t gkh_update_nodes(void* h)
     return (uint32_t)s.GetNodeProxys().size();
 }
 const GkNodeProxy* gkh_node_proxies(void* h) { return ((EngineMirror*)h)->scene.GetNodeProxys().data(); }
+// what the last gkh_update_nodes rewrote: returns -1 when it was a full pass, else the number of proxy indices (see Scene::MarkNodeDirty)
+int64_t gkh_changed_proxies(void* h, const uint32_t** indices)
+{
+    auto& s = ((EngineMirror*)h)->scene;
+    if (s.LastUpdateWasFull()) return -1;
+    *indices = s.ChangedProxies().data();
+    return (int64_t)s.ChangedProxies().size();
+}
 void gkh_mark_dirty(void* h) { ((EngineMirror*)h)->scene.MarkDirty(); }
 void gkh_scene_step(void* h, uint32_t frame) { SceneList::BrickFieldStep(((EngineMirror*)h)->scene, frame); }
 int gkh_set_node_translation(void* h, uint32_t node, float x, float y, float z)
@@ -82,7 +90,7 @@ int gkh_set_node_translation(void* h, uint32_t node, float x, float y, float z)
     if (node >= s.Nodes().size()) return -1;
     s.Nodes()[node]->SetTranslation(vec3(x, y, z));
     s.Nodes()[node]->RecalcTransform(true);
-    s.MarkDirty();
+    s.MarkNodeDirty(node);
     return 0;
 }
 

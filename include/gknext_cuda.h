@@ -144,6 +144,11 @@ GkStatus gk_update_materials(GkContext* ctx, const GkMaterial* materials, uint32
  * (RayTraceBaseRenderer.cpp:176-228).  `refit` != 0 keeps the TLAS topology and only refits
  * boxes (valid when the instance count is unchanged); 0 rebuilds it. */
 GkStatus gk_update_instances(GkContext* ctx, const GkNodeProxy* nodes, uint32_t count, int refit);
+/* The same for a frame in which few nodes changed: proxies[k] replaces the record at indices[k] of the array a previous
+ * gk_update_instances left on the device (the instance count stays), then the instance records, world boxes and the TLAS are
+ * updated as above.  The reference rewrites and re-uploads every proxy on a dirty frame (Scene.cpp:464-511); a MagicaLego
+ * frame moves a handful of bricks (MagicaLegoGameInstance.cpp:746-807): 1 % of 200 000 proxies are 0.4 MB instead of 41 MB. */
+GkStatus gk_update_instances_sparse(GkContext* ctx, const uint32_t* indices, const GkNodeProxy* proxies, uint32_t changed, int refit);
 /* Optional probe grid for the path terminator (Scene.cpp:258-259 buffers; AmbientCube.slang).
  * NULL (the default) means un-baked probes, i.e. all zero. */
 GkStatus gk_set_probes(GkContext* ctx, const GkAmbientCube* cubes, const GkVoxelData* voxels, size_t count);

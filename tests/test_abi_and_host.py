@@ -132,3 +132,36 @@ def test_procedural_scenes_have_the_named_size(built):
     assert 1 <= (before != after).sum() <= 20  # 1 % of the bricks move per frame
     eng = gk.Engine("city", 3, 4, 7, 4)
     assert eng.triangles() == 3 * 12 * 16 + 12 and eng.update_nodes()[1] == 17
+
+
+def _proxy_bytes(nodes, n):
+    import ctypes
+    return np.frombuffer(ctypes.string_at(nodes, n * ctypes.sizeof(gk.GkNodeProxy)), np.uint8).reshape(n, -1).copy()
+
+
+def test_incremental_update_nodes_equals_the_full_pass(built):
+    """Scene::MarkNodeDirty: re-evaluating only the marked and the still-settling nodes must leave the proxy array exactly as
+    the full loop of the reference (Scene.cpp:464-511) writes it, and ChangedProxies() must name every record that differs."""
+    inc, full = gk.Engine("bricks", 3000, 42), gk.Engine("bricks", 3000, 42)
+    for e in (inc, full):
+        e.update_nodes()
+    assert inc.changed_proxies() is None  # the first pass is a full one ...
+    inc.update_nodes(); full.mark_dirty(); full.update_nodes()
+    assert inc.changed_proxies().size == 3001  # ... and every node settles from its placeholder previous transform in the second
+    prev = _proxy_bytes(*inc.update_nodes())
+    for frame in range(1, 7):
+        inc.step_scene(frame)
+        full.step_scene(frame); full.mark_dirty()
+        a, b = _proxy_bytes(*inc.update_nodes()), _proxy_bytes(*full.update_nodes())
+        assert np.array_equal(a, b), f"frame {frame}"
+        changed = inc.changed_proxies()
+        assert changed is not None and full.changed_proxies() is None
+        differs = np.flatnonzero((a != prev).any(axis=1))
+        assert set(differs) <= set(changed.tolist()) and 0 < changed.size <= 2 * 30 + 2
+        prev = a
+    # nothing marked: a frame without motion settles the last movers, then the scene is clean
+    a = _proxy_bytes(*inc.update_nodes()); full.mark_dirty(); b = _proxy_bytes(*full.update_nodes())
+    assert np.array_equal(a, b)
+    inc.set_node_translation(5, 1.0, 0.5, 1.0); full.set_node_translation(5, 1.0, 0.5, 1.0); full.mark_dirty()
+    a, b = _proxy_bytes(*inc.update_nodes()), _proxy_bytes(*full.update_nodes())
+    assert np.array_equal(a, b) and 5 in inc.changed_proxies()

@@ -388,6 +388,36 @@ def test_small_motion_refits_and_teleports_fall_back_to_rebuild(built):
     _compare_hits(r, orc, rays, "bricks teleported (rebuilt)")
 
 
+def test_sparse_instance_update_equals_full_update(built):
+    """gk_update_instances_sparse (C3: only the changed proxies travel, the rest of the array stays on the device) must give the
+    TLAS of a full gk_update_instances: same hits against the reference on the refit path and after the guard forces a rebuild."""
+    eng, r, orc, (nodes, n) = _setup("bricks", 64, 64, (3000, 42))
+    rng = np.random.default_rng(17)
+    rays = _random_rays(rng, 60000, (-20, 0.0, -20), (20, 3.0, 20))
+    rays[:, 5] = -np.abs(rays[:, 5]) - 0.2
+    rejected_seen = False
+    for frame in range(1, 14):
+        eng.step_scene(frame)
+        nodes, n = eng.update_nodes()
+        changed = eng.changed_proxies()
+        assert changed is not None and 0 < changed.size < n // 10
+        staging = (gk.GkNodeProxy * changed.size)(*[nodes[int(i)] for i in changed])
+        r.update_instances_sparse(changed, staging, refit=True)
+        if frame in (1, 2) or (r.bvh_info().refitsRejected > 0 and not rejected_seen):
+            rejected_seen = rejected_seen or r.bvh_info().refitsRejected > 0
+            orc.set_nodes(nodes, n)
+            _attach_reference(orc, eng, nodes, n)
+            _compare_hits(r, orc, rays, f"bricks sparse update f{frame}")
+            if rejected_seen:
+                break
+    assert rejected_seen, "the growth guard never fired: the rebuild branch of the sparse update is untested"
+    # an out-of-range index is refused and leaves the scene usable
+    bad = (gk.GkNodeProxy * 1)(nodes[0])
+    with pytest.raises(RuntimeError):
+        r.update_instances_sparse(np.array([n + 5], np.uint32), bad)
+    _compare_hits(r, orc, rays, "bricks after a refused sparse update")
+
+
 # ---------------------------------------------------------------- hit parity at the sizes BASELINE.json names
 def _subsampled_primary(eng, W, H, stride):
     return np.ascontiguousarray(ol.primary_rays(eng.ubo(W, H), W, H)[::stride])
