@@ -21,6 +21,8 @@
 // Bytes per primitive (roofline model): keys+indices 12 B x (2 + 2x radix passes),
 // boxes 32 B r/w, binary node 40 B, wide node 128 B / ~3 prims.
 #include "gk_context.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -547,13 +549,11 @@ __global__ void k_collapse_seed(Bvh2View B, const uint32_t* __restrict__ groupRo
     rootRef[g] = w;
 }
 
-__global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksIn, uint32_t taskCount, uint32_t* __restrict__ tasksOut,
-                                 uint32_t* __restrict__ counters /* [0]=outCount [1]=wideCount */, WideNode* __restrict__ nodes, uint32_t* __restrict__ nodeSrc,
-                                 uint32_t leafMax, int tlas, uint32_t nodeCapacity)
+// One collapse task: binary node b2 becomes wide node w; its internal children are queued for the next level.
+__device__ __forceinline__ void collapseTask(const Bvh2View& B, uint32_t b2, uint32_t w, uint32_t* __restrict__ tasksOut, uint32_t* __restrict__ outCount,
+                                             uint32_t* __restrict__ wideCount, WideNode* __restrict__ nodes, uint32_t* __restrict__ nodeSrc, uint32_t leafMax, int tlas,
+                                             uint32_t nodeCapacity)
 {
-    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ti >= taskCount) return;
-    const uint32_t b2 = tasksIn[2 * ti], w = tasksIn[2 * ti + 1];
     uint32_t slot[8];
     int cnt = 0;
     if (B.cost) {
@@ -628,8 +628,8 @@ __global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksI
     }
     uint32_t base = 0, tbase = 0;
     if (internal) {
-        base = atomicAdd(&counters[1], (uint32_t)internal);
-        tbase = atomicAdd(&counters[0], (uint32_t)internal);
+        base = atomicAdd(wideCount, (uint32_t)internal);
+        tbase = atomicAdd(outCount, (uint32_t)internal);
     }
     if (w >= nodeCapacity || base + internal > nodeCapacity) return; // capacity is an upper bound; never expected
     WideNode n;
@@ -658,6 +658,33 @@ __global__ void k_collapse_level(Bvh2View B, const uint32_t* __restrict__ tasksI
     const uint4* s = reinterpret_cast<const uint4*>(&n);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = s[i];
+}
+
+// The whole top-down collapse in ONE cooperative launch: the levels are separated by grid-wide barriers instead of a host round trip per
+// level (a 200 k-instance TLAS has about a dozen).  Three queue counters rotate (this level's input, its output, and the one being cleared
+// for the level after), so that no block clears a counter another block still reads.
+constexpr int kCollapseBlock = 128;
+__global__ void __launch_bounds__(kCollapseBlock) k_collapse_all(Bvh2View B, uint32_t* __restrict__ tasksA, uint32_t* __restrict__ tasksB,
+                                                                 uint32_t* __restrict__ counters /* [0],[2],[3] = queue counts, [1] = wideCount */,
+                                                                 WideNode* __restrict__ nodes, uint32_t* __restrict__ nodeSrc, uint32_t leafMax, int tlas,
+                                                                 uint32_t nodeCapacity)
+{
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    const int slotOf[3] = {0, 2, 3};
+    uint32_t* qin = tasksA;
+    uint32_t* qout = tasksB;
+    for (int level = 0;; ++level) {
+        uint32_t* cin = counters + slotOf[level % 3];
+        uint32_t* cout = counters + slotOf[(level + 1) % 3];
+        const uint32_t tasks = *reinterpret_cast<volatile uint32_t*>(cin);
+        if (tasks == 0) break;
+        if (gtid == 0) counters[slotOf[(level + 2) % 3]] = 0;
+        for (uint32_t ti = gtid; ti < tasks; ti += gsize) collapseTask(B, qin[2 * ti], qin[2 * ti + 1], qout, cout, counters + 1, nodes, nodeSrc, leafMax, tlas, nodeCapacity);
+        grid.sync();
+        uint32_t* t = qin;
+        qin = qout, qout = t;
+    }
 }
 
 // Per-axis step exponent: the smallest power of two with extent / step <= 250, but never
@@ -1038,17 +1065,22 @@ static GkStatus collapse(Context& c, Lbvh& T, uint32_t groups, uint32_t leafMax,
     const Bvh2View B = viewOf(T);
     if (!dExplicitRoot) k_group_roots<<<gridFor(n), 256, 0, st>>>(T.keys.p, n, T.first.p, T.last.p, c.dGroupRoot.p, groupShift);
     k_collapse_seed<<<gridFor(groups), 256, 0, st>>>(B, c.dGroupRoot.p, groups, leafMax, tlas ? 1 : 0, dRootRef, c.dTaskA.p, c.dCounters.p);
-    uint32_t* in = c.dTaskA.p;
-    uint32_t* out = c.dTaskB.p;
     uint32_t h[2] = {0, 0};
-    for (int level = 0; level < 128; ++level) {
-        GK_CUDA(cudaMemcpyAsync(h, c.dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-        GK_CUDA(cudaStreamSynchronize(st));
-        const uint32_t tasks = h[0];
-        if (tasks == 0) break;
-        GK_CUDA(cudaMemsetAsync(c.dCounters.p, 0, sizeof(uint32_t), st));
-        k_collapse_level<<<gridFor(tasks, 128), 128, 0, st>>>(B, in, tasks, out, c.dCounters.p, nodes.p, nodeSrc.p, leafMax, tlas ? 1 : 0, capacity);
-        std::swap(in, out);
+    {
+        static int blocksPerSm = 0; // co-resident blocks of the cooperative launch (same for every device this library targets: sm_100a)
+        if (!blocksPerSm) GK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, k_collapse_all, kCollapseBlock, 0));
+        if (c.smCount == 0) GK_CUDA(cudaDeviceGetAttribute(&c.smCount, cudaDevAttrMultiProcessorCount, c.device));
+        const uint32_t wanted = gridFor(n, kCollapseBlock), resident = (uint32_t)std::max(1, blocksPerSm) * (uint32_t)std::max(1, c.smCount);
+        uint32_t* ta = c.dTaskA.p;
+        uint32_t* tb = c.dTaskB.p;
+        uint32_t* cnt = c.dCounters.p;
+        WideNode* np = nodes.p;
+        uint32_t* sp = nodeSrc.p;
+        uint32_t lm = leafMax, cap = capacity;
+        int tl = tlas ? 1 : 0;
+        Bvh2View view = B;
+        void* args[] = {&view, &ta, &tb, &cnt, &np, &sp, &lm, &tl, &cap};
+        GK_CUDA(cudaLaunchCooperativeKernel((const void*)k_collapse_all, dim3(std::min(wanted, resident)), dim3(kCollapseBlock), args, 0, st));
     }
     GK_CUDA(cudaMemcpyAsync(h, c.dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));
@@ -1160,12 +1192,20 @@ GkStatus updateInstances(Context& c, const GkNodeProxy* nodes, uint32_t count, b
     return updateInstancesOnDevice(c, count, refit, evs.e[0], evs.e[1], nodes);
 }
 
+constexpr uint32_t kRefitBackoff = 16;
 // Instance records, world boxes and the TLAS (refit or build) from the node proxies in c.dNodes.
 static GkStatus updateInstancesOnDevice(Context& c, uint32_t count, bool refit, cudaEvent_t e0, cudaEvent_t e1, const GkNodeProxy* nodes)
 {
     cudaStream_t st = c.stream;
     Lbvh& T = c.tlasTree;
     if (refit && (!c.haveInstances || count != T.n)) refit = false;
+    // A scene whose refits keep failing the growth guard (C3: 1 % of 200 k bricks teleport every frame) stops paying for the attempt
+    // (bound propagation + one host round trip for the area): after two rejections in a row the next kRefitBackoff updates rebuild directly.
+    bool guardRebuild = false;
+    if (refit && c.refitRejectedInARow >= 2 && c.refitBackoffLeft > 0) {
+        c.refitBackoffLeft--;
+        refit = false, guardRebuild = true;
+    }
     c.nodeCount = count;
     T.n = count;
     GK_CUDA(T.plo.reserve(count));
@@ -1179,7 +1219,6 @@ static GkStatus updateInstancesOnDevice(Context& c, uint32_t count, bool refit, 
     GK_CUDA(c.dCounters.reserve(8));
     float* dArea = reinterpret_cast<float*>(c.dCounters.p + 4);
     float area = 0.f;
-    bool guardRebuild = false;
     if (refit) {
         // Refit = new boxes on the old topology.  It is kept only while the tree stays good: the summed
         // surface area of the internal nodes may grow to kRefitGrowthLimit x its value at the last build
@@ -1192,10 +1231,12 @@ static GkStatus updateInstancesOnDevice(Context& c, uint32_t count, bool refit, 
         GK_CUDA(cudaStreamSynchronize(st));
         if (area <= kRefitGrowthLimit * c.tlasAreaAtBuild) {
             if (c.tlasNodeCount) k_quantise<<<gridFor(c.tlasNodeCount, 128), 128, 0, st>>>(viewOf(T), c.dTlasNodes.p, c.dTlasSrc.p, c.tlasNodeCount);
+            c.refitRejectedInARow = 0;
         } else {
             refit = false;
             guardRebuild = true;
             c.refitRejected++;
+            if (++c.refitRejectedInARow >= 2) c.refitBackoffLeft = kRefitBackoff;
         }
     }
     if (!refit) {

@@ -283,8 +283,14 @@ bool Scene::UpdateNodes() // Scene.cpp:464-511
         };
         for (uint32_t i : set) // a node whose proxy count changed reshapes the list: full pass below, before anything ticks
             if (i < nodes_.size() && proxyOffset_[i + 1] - proxyOffset_[i] != sections(i)) structural = true;
-        for (uint32_t i : set) {
+        for (size_t k = 0; k < set.size(); ++k) {
+            const uint32_t i = set[k];
             if (structural || i >= nodes_.size()) continue;
+            if (k + 8 < set.size() && set[k + 8] < nodes_.size()) { // the nodes are scattered heap objects: hide the misses
+                const char* ahead = reinterpret_cast<const char*>(nodes_[set[k + 8]].get());
+                for (int line = 0; line < 8; ++line) __builtin_prefetch(ahead + 64 * line);
+                __builtin_prefetch(&nodeProxys_[proxyOffset_[set[k + 8]]]);
+            }
             auto& node = nodes_[i];
             const uint32_t want = sections(i);
             if (!node->IsDrawable()) continue;
