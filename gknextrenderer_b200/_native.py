@@ -219,6 +219,7 @@ HOST_API = {
     "gkh_renderer_delete_swapchain": (C.c_int, [_P]),
     "gkh_renderer_post_load_scene": (C.c_int, [_P]),
     "gkh_renderer_before_next_frame": (C.c_int, [_P]),
+    "gkh_renderer_instance_bytes_uploaded": (C.c_uint64, [_P]),
     "gkh_renderer_render": (C.c_int, [_P]),
     "gkh_renderer_context": (_P, [_P]),
 }

@@ -21,6 +21,9 @@
 // Bytes per primitive (roofline model): keys+indices 12 B x (2 + 2x radix passes),
 // boxes 32 B r/w, binary node 40 B, wide node 128 B / ~3 prims.
 #include "gk_context.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 #include <cub/device/device_radix_sort.cuh>
@@ -1106,22 +1109,37 @@ GkStatus buildBlasForest(Context& c)
     ScopedEvents evs(2);
     cudaEvent_t e0 = evs.e[0], e1 = evs.e[1];
     cudaEventRecord(e0, st);
+    // GK_BUILD_LOG=1: wall-clock of each phase (stream drained between them; the total then includes those drains)
+    const bool log = getenv("GK_BUILD_LOG") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!log) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gk build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     const bool ploc = c.blasPloc && T.n > 2;
     GkStatus s = buildRadixTree(c, T, T.group.p, groups, 64, 0, !ploc);
     if (s != GK_OK) return s;
+    mark("bounds + morton + sort");
     if (ploc) {
         s = plocTopology(c, T, c.blasPlocRadius, true, groups, 42);
         if (s != GK_OK) return s;
+        mark("ploc topology");
     }
     GK_CUDA(c.dTris.reserve(T.n));
     k_write_tri_records<<<gridFor(T.n), 256, 0, st>>>(sceneTriPositions().p, T.order.p, c.dModels.p, T.group.p, T.n, c.dTris.p);
+    mark("triangle records");
     s = propagateBounds(c, T, c.sahCollapse, c.blasLeafMax, c.costTri);
     if (s != GK_OK) return s;
+    mark("bounds + cost table");
     DevBuf<uint32_t> rootRef;
     GK_CUDA(rootRef.reserve(groups));
     s = collapse(c, T, groups, c.blasLeafMax, false, c.dBlasNodes, c.dBlasSrc, c.blasNodeCount, rootRef.p);
     if (s != GK_OK) return s;
     k_model_bounds_from_groups<<<gridFor(groups), 256, 0, st>>>(c.dModels.p, groups, c.dGroupLo.p, c.dGroupHi.p, rootRef.p);
+    mark("collapse + quantise");
     cudaEventRecord(e1, st);
     GK_CUDA(cudaMemcpyAsync(c.models.data(), c.dModels.p, sizeof(ModelInfo) * groups, cudaMemcpyDeviceToHost, st));
     GK_CUDA(cudaStreamSynchronize(st));

@@ -152,8 +152,11 @@ void CudaPathTracingRenderer::BeforeNextFrame()
             sparseStaging_.resize(changed.size());
             for (size_t k = 0; k < changed.size(); ++k) sparseStaging_[k] = px[changed[k]];
             check(gk_update_instances_sparse(ctx_, changed.data(), sparseStaging_.data(), (uint32_t)changed.size(), 1), "gk_update_instances_sparse");
-        } else
+            instanceBytesUploaded_ += changed.size() * (sizeof(GkNodeProxy) + sizeof(uint32_t));
+        } else {
             check(gk_update_instances(ctx_, px.data(), (uint32_t)px.size(), refit ? 1 : 0), "gk_update_instances");
+            instanceBytesUploaded_ += px.size() * sizeof(GkNodeProxy);
+        }
         updatesSinceRebuild_ = refit ? updatesSinceRebuild_ + 1 : 0;
         lastInstanceCount_ = px.size();
         instancesUploaded_ = true;

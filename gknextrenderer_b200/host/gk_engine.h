@@ -101,6 +101,7 @@ public:
     // scene load boundary: called where Scene::RebuildMeshBuffer runs (Scene.cpp:101)
     void OnPostLoadScene();
     GkContext* Context() { return ctx_; }
+    uint64_t InstanceBytesUploaded() const { return instanceBytesUploaded_; } // host->device bytes of all instance updates so far
     VkExtent2D Extent() const { return extent_; }
     void SetTile(uint32_t index, uint32_t count, uint32_t rows) { tileIndex_ = index, tileCount_ = count, tileRows_ = rows; }
     void SetTraceAllRows(bool on) { traceAllRows_ = on; } // frame-sharded progressive rendering (GK_CFG_TRACE_ALL_ROWS)
@@ -118,6 +119,7 @@ private:
     bool instancesUploaded_ = false;
     size_t lastInstanceCount_ = 0;
     std::vector<GkNodeProxy> sparseStaging_;
+    uint64_t instanceBytesUploaded_ = 0;
     uint32_t updatesSinceRebuild_ = 0;
 };
 

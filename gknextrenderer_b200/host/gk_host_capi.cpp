@@ -156,6 +156,7 @@ int gkh_renderer_delete_swapchain(void* r) { GKH_TRY(((HostRenderer*)r)->r.Delet
 int gkh_renderer_post_load_scene(void* r) { GKH_TRY(((HostRenderer*)r)->r.OnPostLoadScene()) }
 int gkh_renderer_before_next_frame(void* r) { GKH_TRY(((HostRenderer*)r)->r.BeforeNextFrame()) }
 int gkh_renderer_render(void* r) { GKH_TRY(((HostRenderer*)r)->r.Render(nullptr, 0)) }
+uint64_t gkh_renderer_instance_bytes_uploaded(void* r) { return ((HostRenderer*)r)->r.InstanceBytesUploaded(); }
 void* gkh_renderer_context(void* r) { return ((HostRenderer*)r)->r.Context(); }
 
 } // extern "C"
