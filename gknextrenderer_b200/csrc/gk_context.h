@@ -247,7 +247,7 @@ struct Context {
     bool primaryLaneKernel = true;   // wave 0 (coherent camera rays) on the while-while lane kernel
     bool tailCoop = true;            // ... with eight lanes per path (k_tail_coop) instead of one
     uint32_t streamTailPaths = 262144; // streamed wave loop: finish the frame in one k_tail launch once at most this many rays are in flight
-    uint32_t schedMinRays = 0;       // waves smaller than this keep the variant-0 kernels
+    uint32_t schedMinRays = 1000000; // waves of fewer live paths than this run on the one-ray-per-lane kernel (swept 0 .. 1 M on 1/1 .. 1/8 frame shares: -0.2 % .. -7 %)
     int schedBlocksPerSm = 0, smCount = 0;
     static constexpr uint32_t kCursorCount = 1024;
     uint32_t* dCursors = nullptr;    // one zeroed queue cursor per launch of a frame

@@ -796,6 +796,13 @@ static void launchCoopBounded(Context& c, const SceneView& V, const RayIO& io, u
     launchMapped<kAnyHit, true>(stream, grid, 256, V, io, bound, c.travStats ? c.dTravStats : nullptr, countPtr);
 }
 
+// Mid-size waves of the streamed loop (sched_min_rays): the one-ray-per-lane kernel, sized by an upper bound.
+template <bool kAnyHit, class RayIO>
+static void launchLaneBounded(Context& c, const SceneView& V, const RayIO& io, uint32_t bound, cudaStream_t stream, const uint32_t* countPtr)
+{
+    launchMapped<kAnyHit, false>(stream, std::max(1u, (bound + c.laneBlock - 1) / c.laneBlock), c.laneBlock, V, io, bound, c.travStats ? c.dTravStats : nullptr, countPtr);
+}
+
 // Next zeroed fetch cursor of the frame (the block of cursors is cleared once per frame / per intersect call).
 static uint32_t* nextCursor(Context& c, cudaStream_t)
 {
@@ -835,7 +842,7 @@ static void launchTraceIO(Context& c, const SceneView& V, const RayIO& io, uint3
         launchSched<kAnyHit>(c, V, io, count, stream);
         return;
     }
-    const bool coop = count < c.coopThreshold;
+    const bool coop = count < std::min(c.coopThreshold, 65536u); // one-shot batches: the cooperative mapping pays below 65 k rays (r01 sweep)
     const unsigned per = coop ? kRaysPerBlock : c.laneBlock; // rays per block
     const unsigned grid = (count + per - 1) / per;
     TraversalStats* ts = c.travStats ? c.dTravStats : nullptr;
@@ -1126,31 +1133,40 @@ static GkStatus traceFrameStreamed(Context& c)
         // waves below the threshold: the eight-lanes-per-ray kernel (a lone ray finishes ~4x sooner than on one lane); `bound` is
         // the size of an earlier wave, so a wave is only classed small when it certainly is
         const bool small = wave > 0 && bound < std::min(c.coopThreshold, n / 4u); // relative too: a rank of an 8-GPU frame has 0.26 M paths in all
+        // waves too small to keep the persistent warps of the scheduled kernel fed (a rank's share of a multi-GPU frame, Cornell):
+        // its refill/vote machinery then costs more than the divergence it removes, and the plain lane kernel is faster
+        const bool mid = !small && wave > 0 && bound < c.schedMinRays && !c.travStats;
+        auto traceE = [&](cudaStream_t on) {
+            if (small) launchCoopBounded<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, on, c.extendQ[cur].count);
+            else if (mid) launchLaneBounded<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, on, c.extendQ[cur].count);
+            else launchSched<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, on, c.extendQ[cur].count);
+        };
+        auto traceS = [&](cudaStream_t on) {
+            if (small) launchCoopBounded<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, on, c.shadowQ[cur].count);
+            else if (mid) launchLaneBounded<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, on, c.shadowQ[cur].count);
+            else launchSched<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, on, c.shadowQ[cur].count);
+        };
         size_t b, d, s0 = 0, s1 = 0;
         if (fork) {
             GK_CUDA(cudaEventRecord(c.evFork, st));
             GK_CUDA(cudaStreamWaitEvent(c.stream2, c.evFork, 0));
             s0 = markOn(c.stream2);
-            if (small) launchCoopBounded<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, c.stream2, c.shadowQ[cur].count);
-            else launchSched<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, c.stream2, c.shadowQ[cur].count);
+            traceS(c.stream2);
             s1 = markOn(c.stream2);
             GK_CUDA(cudaEventRecord(c.evJoin, c.stream2));
-            if (small) launchCoopBounded<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, st, c.extendQ[cur].count);
-            else launchSched<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, st, c.extendQ[cur].count);
+            traceE(st);
             b = mark();
             GK_CUDA(cudaStreamWaitEvent(st, c.evJoin, 0));
             d = mark();
             fs.launches += 2;
         } else {
-            if (small) launchCoopBounded<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, st, c.extendQ[cur].count);
             // camera rays are coherent: the while-while lane kernel needs ~30 % fewer instructions on them (3.1 vs 2.4 Grays/s on C2)
-            else if (wave == 0 && c.primaryLaneKernel && !c.travStats) launchMapped<false, false>(st, gridFor(sizeE, c.laneBlock), c.laneBlock, V, QueueIO{c.extendQ[cur]}, sizeE, nullptr);
-            else launchSched<false>(c, V, QueueIO{c.extendQ[cur]}, sizeE, st, c.extendQ[cur].count);
+            if (!small && wave == 0 && c.primaryLaneKernel && !c.travStats) launchMapped<false, false>(st, gridFor(sizeE, c.laneBlock), c.laneBlock, V, QueueIO{c.extendQ[cur]}, sizeE, nullptr);
+            else traceE(st);
             fs.launches++;
             b = mark();
             if (sizeS) {
-                if (small) launchCoopBounded<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, st, c.shadowQ[cur].count);
-                else launchSched<true>(c, V, ShadowIO{c.shadowQ[cur]}, sizeS, st, c.shadowQ[cur].count);
+                traceS(st);
                 fs.launches++;
             }
             d = mark();

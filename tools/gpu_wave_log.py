@@ -8,8 +8,10 @@ from bench import WORKLOADS
 name = sys.argv[1] if len(sys.argv) > 1 else "room"
 scene, args, W, H, settings = WORKLOADS[name]
 eng = gk.Engine(scene, *args); eng.set(**settings)
-r = gk.Renderer(W, H, device=0); r.load(eng)
-for k, v in [a.split("=") for a in sys.argv[2:]]:
+opts = dict(a.split("=") for a in sys.argv[2:])
+tiles = int(opts.pop("tiles", 1))  # >1: the share one rank of a tile-partitioned frame traces
+r = gk.Renderer(W, H, device=0, tile_index=0, tile_count=tiles, tile_rows=16); r.load(eng)
+for k, v in opts.items():
     r.set_option(k, float(v))
 os.environ.pop("GK_WAVE_LOG")
 for f in range(3):
