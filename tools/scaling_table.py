@@ -1,17 +1,20 @@
-"""profiles/r01_bench/n<N>_<workload>.json -> profiles/r01_scaling.md"""
+"""profiles/<round>_bench/n<N>_<workload>.json -> profiles/<round>_scaling.md      python tools/scaling_table.py [r02]"""
 import glob
 import json
 import os
+import sys
+
+ROUND = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rows = {}
-for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench", "n*_*.json"))):
+for f in sorted(glob.glob(os.path.join(ROOT, "profiles", ROUND + "_bench", "n*_*.json"))):
     d = json.load(open(f))
     if d.get("impl") == "reference":
         continue
     mode = "frames" if d.get("scaling") == "weak" else "tiles"
     rows.setdefault((d["config"]["workload"].split(":")[0], mode), {})[d["n_gpus"]] = d
-out = ["# Round 1: throughput and scaling on B200 (bench.py, 20 timed frames after 5 warm-up frames)\n",
+out = [f"# Round {int(ROUND[1:])}: throughput and scaling on B200 (bench.py, 20 timed frames after 5 warm-up frames)\n",
        "`value` = rays traced by all ranks / max-over-ranks device time; `e2e` adds the UBO upload and the read-back of the final image on the presenting rank.",
        "Speed-ups are against the 1-GPU line of the same workload; the driver computes its own from the per-N values.\n"]
 for (wl, mode), by_n in sorted(rows.items()):
@@ -36,7 +39,19 @@ for (wl, mode), by_n in sorted(rows.items()):
         c = base["cpu_baseline"]
         out.append(f"\nCPU baseline on the same box: {c['value']:.1f} Mrays/s on {c['cores']} cores ({c['kind']}: {c['sample']}).")
     out.append("")
-out.append("Note: the 2- and 4-GPU lines of C2 and the multi-GPU lines of C4 were measured before the last change of the round (tight world boxes of rotated "
-           "instances: -7 % frame time on one GPU for C2, neutral for C4 whose instances are axis aligned); the 1-GPU lines and the 8-GPU line of C2 are final.")
-open(os.path.join(ROOT, "profiles", "r01_scaling.md"), "w").write("\n".join(out) + "\n")
+if ROUND == "r01":
+    out.append("Note: the 2- and 4-GPU lines of C2 and the multi-GPU lines of C4 were measured before the last change of the round (tight world boxes of rotated "
+               "instances: -7 % frame time on one GPU for C2, neutral for C4 whose instances are axis aligned); the 1-GPU lines and the 8-GPU line of C2 are final.")
+else:
+    # the C4 results that ride on the C2 lines at N > 1 (bench.py "secondary")
+    out.append("## C4 city 4K progressive, measured inside the N-GPU runs of C2 (`secondary` of the bench line)\n")
+    out.append("| GPUs | shard | Mrays/s | ms/step | speed-up vs one GPU of the same run | e2e Mrays/s | exchange ms |")
+    out.append("|---:|---|---:|---:|---:|---:|---:|")
+    for (wl, mode), by_n in sorted(rows.items()):
+        for n in sorted(by_n):
+            for sec in by_n[n].get("secondary") or []:
+                out.append(f"| {sec['n_gpus']} | {sec['shard']} | {sec['value']:.0f} | {sec['ms_per_step']:.2f} | {sec['speedup_vs_one_gpu_same_run']:.2f}x "
+                           f"(1 GPU: {sec['one_gpu_same_run']['value']:.0f}) | {sec['e2e']['value']:.0f} | {sec['breakdown_ms_per_step'].get('xchg', 0):.2f} |")
+    out.append("")
+open(os.path.join(ROOT, "profiles", ROUND + "_scaling.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
