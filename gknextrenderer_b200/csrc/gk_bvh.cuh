@@ -192,9 +192,11 @@ __device__ __forceinline__ bool childTest(const NodeFrame& F, const PlaneSel& S,
     return tn <= tf * kBoxTolerance;
 }
 
-// NOTE (round 2): traverseCoop / traverseLane are the round-1 kernels, kept byte for byte as trace variant 0 (the A/B
-// baseline of the scheduled kernel in gk_trace_sched.cuh, which is the production path and reports stack overflow
-// through SceneView::overflowFlag).  Adding an overflow store to traverseLane made ptxas address the local-memory stack
+// NOTE (round 2): traverseCoop / traverseLane are the round-1 kernels (camera rays, small and mid-size waves, the tail, ray
+// casts, the probe baker; the scheduled kernel in gk_trace_sched.cuh carries the large waves and reports stack overflow through
+// SceneView::overflowFlag).  The only change since round 1: child pushes stop one entry short of the end, so that the
+// return-to-TLAS sentinel always finds a slot - a full stack can drop a far child (a lost hit, flagged by the statistics)
+// but can no longer lose the marker and index the BLAS with a TLAS entry.  Adding an overflow store to traverseLane made ptxas address the local-memory stack
 // through a uniform register that the code after the loop reuses; lanes leaving the any-hit loop early then corrupted
 // the stack base of the lanes still inside (compute-sanitizer: invalid __local__ read at the tuv pointer's low word +
 // 8*sp).  These two functions only report a dropped entry through the traversal statistics (maxStack).
@@ -236,7 +238,7 @@ __device__ __forceinline__ bool traverseCoop(const SceneView& S, f3 O, f3 Dn, fl
                 const uint32_t key = __reduce_min_sync(gmask, hitBox ? ((__float_as_uint(tn) & ~7u) | sub) : 0xffffffffu);
                 const unsigned near = key & 7u;
                 const unsigned others = m & ~(1u << near);
-                const int room = kStackSize - sp;
+                const int room = kStackSize - 1 - sp; // the last slot is reserved for the return-to-TLAS sentinel
                 if (hitBox && sub != near) {
                     const int rank = __popc(others & ((1u << sub) - 1u));
                     if (rank < room) stackRow[sp + rank] = make_uint2(ref, __float_as_uint(tn));
@@ -378,7 +380,7 @@ __device__ __forceinline__ bool traverseLane(const SceneView& S, f3 O, f3 Dn, fl
                         uint32_t pr = ref;
                         float pt = tn;
                         if (tn < bestT) { pr = bestRef, pt = bestT, bestRef = ref, bestT = tn; }
-                        if (pr != kInvalid && sp < kStackSize) stk.e[sp++] = make_uint2(pr, __float_as_uint(pt));
+                        if (pr != kInvalid && sp < kStackSize - 1) stk.e[sp++] = make_uint2(pr, __float_as_uint(pt)); // last slot: sentinel only
                         else if (kStats && pr != kInvalid) stats->maxStack = kStackSize + 1; // an entry was dropped
                     }
                 }
