@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the path-tracing hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload room|cornell|city|bricks]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload room|roomu|cornell|city|city400|bricks]
 
 A "step" is one frame of the hot path on synthetic input: per-frame UBO -> wavefront path tracer
 (generate / extend / shade / shadow / accumulate) -> fused temporal reprojection -> joint bilateral
@@ -41,6 +41,9 @@ WORKLOADS = {
     "bricks": ("bricks", (200000, 42), 1920, 1080, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=1, TAA=1)),
     # progressive accumulation, denoiser off: the state gkNextBenchmark runs in (gkNextBenchmark.cpp:16-31); one step = 1 of the 64 spp
     "city": ("city", (40, 100, 7, 46), 3840, 2160, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=0, TAA=0, ProgressiveRender=1)),
+    # the city with 400 building variants instead of 40: 10.2 M UNIQUE triangles (1.3 GB of triangle records + BVH), 254 M instanced -
+    # BASELINE.json configs[4]'s "100M-triangle scene" class; frame-sharded at N > 1 with --shard frames
+    "city400": ("city", (400, 100, 7, 46), 3840, 2160, dict(NumberOfSamples=1, NumberOfBounces=4, TemporalFrames=16, Denoiser=0, TAA=0, ProgressiveRender=1)),
 }
 WORKLOAD_NAMES = {
     "room": "C2: procedural 1M-triangle room (1280 instances of 6 meshes), 1920x1080, 1 spp, 4 bounces, sun+sky, reproject + JBF",
@@ -48,6 +51,7 @@ WORKLOAD_NAMES = {
     "cornell": "C1: built-in Cornell box, 640x360, 8 spp, 4 bounces",
     "bricks": "C3: 200k instanced bricks, per-frame TLAS refit, 1920x1080, 1 spp, 4 bounces",
     "city": "C4: 10M-triangle instanced city, 3840x2160, progressive (1 of 64 spp per step), 4 bounces, denoiser off",
+    "city400": "C4u: city with 400 building variants (10.2 M unique / 254 M instanced triangles), 3840x2160, progressive (1 of 64 spp per step), 4 bounces, denoiser off",
 }
 TILE_ROWS = 16  # rows per tile of the multi-GPU partition; main() shrinks it so that every rank gets >= 32 tiles
 METRIC = "path-tracing throughput (rays traced per second, whole frame incl. reproject + denoise) and ms/frame at the named resolution"
