@@ -215,6 +215,7 @@ struct Context {
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evCopyReady = nullptr, evCopyDone = nullptr;
     const void* asyncCopySrc = nullptr; // non-null while a copy may be in flight
+    int microTiles = 2; // path order: 0 rows, 1 = 8 x 4 pixel blocks per warp, 2 = additionally 16 x 16 squares per thread block (option "micro_tiles")
     uint32_t refitRejectedInARow = 0, refitBackoffLeft = 0; // see updateInstancesOnDevice
     float tlasAreaAtBuild = 0.f;    // summed internal-node area of the TLAS when it was last built
     uint32_t refitRejected = 0;     // refits that degraded the tree too much and became rebuilds

@@ -40,6 +40,7 @@ struct FrameParams {
     uint32_t width, height;
     uint32_t tileIndex, tileCount, tileRows;
     uint32_t pathCount;
+    uint32_t microTiles; // paths of a warp cover an 8 x 4 pixel block instead of a 32 x 1 strip (see pathToPixel)
 };
 
 struct PlaneView {
@@ -67,7 +68,24 @@ __device__ __forceinline__ void storeHalf4(__half* plane, uint32_t pixel, float 
 
 __device__ __forceinline__ uint32_t pathToPixel(const FrameParams& P, uint32_t path)
 {
-    const uint32_t lr = path / P.width, x = path - lr * P.width;
+    uint32_t lr = path / P.width, x = path - lr * P.width;
+    if (P.microTiles) {
+        // Within every band of four rows the paths run through 8 x 4 pixel blocks, one block per warp: camera rays of a warp
+        // then span a compact window of the image (more coherent traversal, more shared cache lines of the scene) and the G-buffer
+        // stores of a warp are four 64-byte row segments.  Needs width % 8 == 0 and tileRows % 4 == 0 (else the linear order).
+        if (P.microTiles == 2) {
+            // 16-row bands: a thread block (256 paths) covers a 16 x 16 pixel square made of 2 x 4 warp blocks
+            const uint32_t band = lr >> 4, q = (lr & 15u) * P.width + x;
+            const uint32_t sq = q >> 8, t = q & 255u, w = t >> 5, l = t & 31u;
+            x = sq * 16u + (w & 1u) * 8u + (l & 7u);
+            lr = band * 16u + (w >> 1) * 4u + (l >> 3);
+        } else {
+            const uint32_t band = lr >> 2, q = (lr & 3u) * P.width + x; // position inside the band of 4 rows
+            const uint32_t blk8 = q >> 5, l = q & 31u;
+            x = blk8 * 8u + (l & 7u);
+            lr = band * 4u + (l >> 3);
+        }
+    }
     const uint32_t blk = lr / P.tileRows, within = lr - blk * P.tileRows;
     const uint32_t row = (blk * P.tileCount + P.tileIndex) * P.tileRows + within;
     return row < P.height ? row * P.width + x : kInvalid;
@@ -1030,7 +1048,7 @@ static GkStatus traceFrameStreamed(Context& c)
 {
     cudaStream_t st = c.stream;
     const uint32_t n = c.pathCount;
-    FrameParams P{c.width, c.height, c.traceTileIndex, c.traceTileCount, c.tileRows, n};
+    FrameParams P{c.width, c.height, c.traceTileIndex, c.traceTileCount, c.tileRows, n, (c.microTiles == 2 && c.width % 16 == 0 && c.tileRows % 16 == 0) ? 2u : (c.microTiles && c.width % 8 == 0 && c.tileRows % 4 == 0) ? 1u : 0u};
     const SceneView V = c.view();
     const ShadeScene SS = shadeSceneOf(c);
     const PlaneView PL = planeViewOf(c);
@@ -1269,7 +1287,7 @@ GkStatus traceFrame(Context& c)
     c.tracedSinceFilter = true;
     if (c.traceVariant == 1) return traceFrameStreamed(c);
     const uint32_t n = c.pathCount;
-    FrameParams P{c.width, c.height, c.traceTileIndex, c.traceTileCount, c.tileRows, n};
+    FrameParams P{c.width, c.height, c.traceTileIndex, c.traceTileCount, c.tileRows, n, (c.microTiles == 2 && c.width % 16 == 0 && c.tileRows % 16 == 0) ? 2u : (c.microTiles && c.width % 8 == 0 && c.tileRows % 4 == 0) ? 1u : 0u};
     const SceneView V = c.view();
     const ShadeScene SS = shadeSceneOf(c);
     const PlaneView PL = planeViewOf(c);
