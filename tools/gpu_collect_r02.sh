@@ -18,7 +18,7 @@ done
 python tools/ncu_summary.py report $O/other_room.ncu-rep > $O/shade_filters_full.md
 rm -f $O/other_room.ncu-rep $O/trace_roomu.ncu-rep
 python tools/bench_filters.py 20 > $O/filters_sweep.jsonl 2> $O/filters_sweep.err
-for wl in room roomu city bricks cornell; do
+for wl in room roomu city city400 bricks cornell; do
   timeout 400 python bench.py --workload $wl > $O/n1_${wl}_tiles.json 2> $O/n1_${wl}_tiles.err
 done
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $O/n1_room_reference.json 2> $O/n1_room_reference.err
