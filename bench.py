@@ -258,6 +258,8 @@ def run(args, workload, shard, steps, warmup, rank, world, local_rank, secondary
         exchange_mode = "nccl all-gather"
         if os.environ.get("GK_EXCHANGE", "p2p") == "p2p" and comp.enable_peer_exchange(r, rank, world):
             exchange_mode = "peer-to-peer push over NVLink (CUDA IPC) between two 4-byte all-reduce barriers"
+            if comp._hkey(r) in comp._nativeComp:
+                exchange_mode += "; sequenced in C++ by lib/libgknext_comp.so on its own NCCL communicator (include/gknext_compositor.h)"
 
     local_filters = world > 1 and exchange_mode.startswith("peer") and settings.get("ProgressiveRender", 0) == 1 and settings.get("Denoiser", 1) == 0
     if local_filters:

@@ -45,6 +45,17 @@ def host_lib():
     return _host
 
 
+_comp = None
+
+
+def comp_lib():
+    """lib/libgknext_comp.so: the multi-GPU compositor over NCCL (include/gknext_compositor.h)."""
+    global _comp
+    if _comp is None:
+        _comp = N.load_comp()
+    return _comp
+
+
 def plane_dtype(name: str):
     """(numpy dtype, channels) of a plane as gk_readback returns it."""
     if name in ("OBJECT_ID0", "OBJECT_ID1", "RAY_COUNT"):

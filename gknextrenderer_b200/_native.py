@@ -16,6 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
 CUDA_LIB_PATH = os.path.join(LIB_DIR, "libgknext_cuda.so")
 HOST_LIB_PATH = os.path.join(LIB_DIR, "libgknext_host.so")
+COMP_LIB_PATH = os.path.join(LIB_DIR, "libgknext_comp.so")
+GKC_UNIQUE_ID_BYTES = 128
 
 GK_EXCHANGE_IPC_BYTES = 8 * 64
 GK_OK = 0
@@ -239,6 +241,29 @@ def load_cuda():
             f"{CUDA_LIB_PATH} is missing: build it with gknextrenderer_b200/build.sh (or __graft_entry__.build()). "
             "There is no CPU fallback for the path-tracing hot path.")
     return _bind(C.CDLL(CUDA_LIB_PATH, mode=C.RTLD_GLOBAL), CUDA_API)
+
+
+# every symbol include/gknext_compositor.h declares
+COMP_API = {
+    "gkc_last_error": (C.c_char_p, []),
+    "gkc_get_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "gkc_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(_P)]),
+    "gkc_enable_frame_sharding": (C.c_int, [_P]),
+    "gkc_barrier": (C.c_int, [_P]),
+    "gkc_composite_frame": (C.c_int, [_P]),
+    "gkc_composite_final": (C.c_int, [_P, C.c_int]),
+    "gkc_composite_frame_shard": (C.c_int, [_P, C.c_int]),
+    "gkc_world": (C.c_int, [_P]),
+    "gkc_rank": (C.c_int, [_P]),
+    "gkc_destroy": (None, [_P]),
+}
+
+
+def load_comp():
+    load_cuda()
+    if not os.path.exists(COMP_LIB_PATH):
+        raise RuntimeError(f"{COMP_LIB_PATH} is missing: build it with gknextrenderer_b200/build.sh")
+    return _bind(C.CDLL(COMP_LIB_PATH), COMP_API)
 
 
 def load_host():

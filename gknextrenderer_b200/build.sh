@@ -22,4 +22,7 @@ for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 $NVCC $ARCH -shared -o lib/libgknext_cuda.so "${objs[@]}" -lcudart
 g++ -O2 -std=c++17 -fPIC -shared -Wall -o lib/libgknext_host.so host/gk_assets.cpp host/gk_engine.cpp host/gk_host_capi.cpp \
     -pthread -Llib -lgknext_cuda -Wl,-rpath,'$ORIGIN'
-echo "built lib/libgknext_cuda.so lib/libgknext_host.so"
+# the multi-GPU compositor over NCCL (include/gknext_compositor.h); NCCL headers/libs: the system package of this image
+g++ -O2 -std=c++17 -fPIC -shared -Wall -o lib/libgknext_comp.so host/gk_compositor.cpp -I/usr/local/cuda/include \
+    -Llib -lgknext_cuda -L/usr/local/cuda/lib64 -lcudart -lnccl -Wl,-rpath,'$ORIGIN'
+echo "built lib/libgknext_cuda.so lib/libgknext_host.so lib/libgknext_comp.so"

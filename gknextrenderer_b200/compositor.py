@@ -95,15 +95,55 @@ _staging = {}
 _p2p = {}
 
 
+_nativeComp = {}  # context handle -> GkCompositor* (lib/libgknext_comp.so)
+
+
+def _hkey(renderer):
+    return renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+
+
+def _gkc(status, lib):
+    if status != 0:
+        raise RuntimeError(f"compositor: {lib.gkc_last_error().decode()} (status {status})")
+
+
+def enable_native(renderer, rank: int, world: int, group=None) -> bool:
+    """The compositor of include/gknext_compositor.h: its own NCCL communicator on the library stream, created from a unique id
+    that rank 0 draws and torch.distributed merely carries to the other ranks.  After this, composite_frame / composite_final /
+    composite_frame_shard are ONE C call each (barrier, peer-to-peer push, barrier - all enqueued from C++)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _native as N, comp_lib
+    lib = comp_lib()
+    ident = (C.c_ubyte * N.GKC_UNIQUE_ID_BYTES)()
+    if rank == 0:
+        _gkc(lib.gkc_get_unique_id(ident, N.GKC_UNIQUE_ID_BYTES), lib)
+    box = [bytes(ident)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ident = (C.c_ubyte * N.GKC_UNIQUE_ID_BYTES).from_buffer_copy(box[0])
+    comp = C.c_void_p()
+    status = lib.gkc_create(renderer.h, rank, world, ident, N.GKC_UNIQUE_ID_BYTES, C.byref(comp))
+    if status != 0:
+        print(f"[compositor] rank {rank}: native compositor unavailable ({lib.gkc_last_error().decode()})", flush=True)
+        return False
+    _nativeComp[_hkey(renderer)] = comp
+    return True
+
+
 def enable_peer_exchange(renderer, rank: int, world: int, group=None) -> bool:
     """Map the exchange planes of all ranks into this process (CUDA IPC) so that composite_frame can
     push rows straight into the peers.  Returns False (and keeps the NCCL all-gather path) when the
-    handles cannot be opened, e.g. no peer access between the devices."""
+    handles cannot be opened, e.g. no peer access between the devices.
+    GK_COMPOSITOR=native (default) drives the exchange from lib/libgknext_comp.so (C++ over NCCL); GK_COMPOSITOR=torch keeps the
+    choreography in this file (torch.distributed barriers around the same push kernels)."""
+    import os
     import torch
     import torch.distributed as dist
     if world == 1:
         return False
     from . import _native as N
+    if os.environ.get("GK_COMPOSITOR", "native") == "native" and dist.get_backend(group) == "nccl":
+        return enable_native(renderer, rank, world, group)
     dev = torch.device(f"cuda:{torch.cuda.current_device()}")
     mine = torch.frombuffer(bytearray(renderer.exchange_ipc_handles()), dtype=torch.uint8).to(dev)
     every = torch.empty(world * N.GK_EXCHANGE_IPC_BYTES, dtype=torch.uint8, device=dev)
@@ -136,6 +176,10 @@ def composite_frame(renderer, rank: int, world: int, tile_rows: int, planes=None
     if world == 1:
         return 0
     hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if hkey in _nativeComp:
+        from . import comp_lib
+        _gkc(comp_lib().gkc_composite_frame(_nativeComp[hkey]), comp_lib())
+        return renderer.exchange_bytes()
     if hkey in _p2p:
         # peer-to-peer: barrier (every rank is done reading last frame's planes) -> one kernel stores the
         # owned rows into all peers over NVLink -> barrier (all rows have landed).  The barriers are
@@ -173,6 +217,10 @@ def composite_final(renderer, rank: int, world: int, dst_rank: int = -1, group=N
     if world == 1:
         return 0
     hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if hkey in _nativeComp:
+        from . import comp_lib
+        _gkc(comp_lib().gkc_composite_final(_nativeComp[hkey], dst_rank), comp_lib())
+        return renderer.plane_bytes("DENOISED") // world
     if hkey not in _p2p:
         raise RuntimeError("composite_final needs enable_peer_exchange() to have succeeded")
     token, stream = _p2p[hkey]
@@ -194,6 +242,11 @@ def enable_frame_sharding(renderer, rank: int, world: int, group=None) -> bool:
     import torch
     import torch.distributed as dist
     hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if world > 1 and hkey in _nativeComp:
+        from . import comp_lib
+        _gkc(comp_lib().gkc_enable_frame_sharding(_nativeComp[hkey]), comp_lib())
+        _shard.add(hkey)
+        return True
     if world == 1 or hkey not in _p2p:
         return False
     dev = torch.device(f"cuda:{torch.cuda.current_device()}")
@@ -215,6 +268,10 @@ def composite_frame_shard(renderer, rank: int, world: int, dst_rank: int = 0, gr
     hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
     if hkey not in _shard:
         raise RuntimeError("composite_frame_shard needs enable_frame_sharding()")
+    if hkey in _nativeComp:
+        from . import comp_lib
+        _gkc(comp_lib().gkc_composite_frame_shard(_nativeComp[hkey], dst_rank), comp_lib())
+        return 3 * 8 * renderer.width * renderer.height * (world - 1) // world
     token, stream = _p2p[hkey]
     renderer.readback_wait()
     with torch.cuda.stream(stream):
@@ -235,6 +292,13 @@ def release(renderer, group=None):
     The exchange has to be enabled again afterwards."""
     import torch.distributed as dist
     hkey = renderer.h.value if hasattr(renderer.h, "value") else int(renderer.h)
+    if hkey in _nativeComp:  # gkc_destroy is the collective tear-down (close peers, barrier, communicator)
+        from . import comp_lib
+        comp_lib().gkc_destroy(_nativeComp.pop(hkey))
+        _shard.discard(hkey)
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier(group=group)
+        return
     had = hkey in _p2p or hkey in _shard
     _p2p.pop(hkey, None)
     _shard.discard(hkey)

@@ -33,6 +33,25 @@ def test_header_symbols_are_exported(built):
     assert gk.cuda_lib().gk_abi_version() == 1
 
 
+def test_compositor_header_symbols_are_exported(built):
+    """include/gknext_compositor.h (multi-GPU compositor over NCCL, lib/libgknext_comp.so): every declared symbol is exported and bound;
+    no collective is called here (that needs GPUs) - only the argument checks that run before any NCCL call."""
+    hdr = open(os.path.join(ROOT, "include", "gknext_compositor.h")).read()
+    declared = set(re.findall(r"\b(gkc_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 10
+    lib = C.CDLL(N.COMP_LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in gknext_compositor.h but not exported"
+    assert declared == set(N.COMP_API), declared ^ set(N.COMP_API)
+    comp = gk.comp_lib()
+    out = C.c_void_p()
+    ident = (C.c_ubyte * N.GKC_UNIQUE_ID_BYTES)()
+    assert comp.gkc_create(None, 0, 2, ident, N.GKC_UNIQUE_ID_BYTES, C.byref(out)) < 0 and b"invalid argument" in comp.gkc_last_error()
+    assert comp.gkc_get_unique_id(ident, 8) < 0
+    assert comp.gkc_composite_frame(None) < 0 and comp.gkc_world(None) == 0 and comp.gkc_rank(None) == -1
+    comp.gkc_destroy(None)
+
+
 def test_pod_layouts_match_reference():
     U = N.GkUniformBufferObject
     assert C.sizeof(U) == 784

@@ -606,8 +606,11 @@ def test_two_gpu_tile_frame_equals_single_gpu_frame(built):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for mode, check, port in (("p2p", "temporal", 29531), ("nccl", "temporal", 29532), ("p2p", "progressive", 29533), ("p2p", "frames", 29534)):
-        env = dict(os.environ, GK_EXCHANGE=mode, GK_CHECK_MODE=check)
+    # GK_COMPOSITOR: "native" = lib/libgknext_comp.so sequences the exchange from C++ on its own NCCL communicator (the default),
+    # "torch" = the same kernels between torch.distributed barriers
+    for mode, check, port, driver in (("p2p", "temporal", 29531, "native"), ("nccl", "temporal", 29532, "torch"), ("p2p", "progressive", 29533, "native"),
+                                      ("p2p", "frames", 29534, "native"), ("p2p", "temporal", 29535, "torch"), ("p2p", "frames", 29536, "torch")):
+        env = dict(os.environ, GK_EXCHANGE=mode, GK_CHECK_MODE=check, GK_COMPOSITOR=driver)
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
                               os.path.join(root, "tools", "multi_gpu_check.py")], env=env, capture_output=True, text=True, timeout=300)
         print(out.stdout[-2000:])

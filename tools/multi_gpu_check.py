@@ -38,9 +38,9 @@ def main():
         ref.update_instances(nodes, n)
     mode = "nccl all-gather"
     if os.environ.get("GK_EXCHANGE", "p2p") == "p2p" and comp.enable_peer_exchange(r, rank, world):
-        mode = "peer-to-peer push"
+        mode = "peer-to-peer push" + (" (native compositor)" if comp._hkey(r) in comp._nativeComp else " (torch barriers)")
     if frames_mode:
-        assert mode == "peer-to-peer push" and comp.enable_frame_sharding(r, rank, world)
+        assert mode.startswith("peer-to-peer push") and comp.enable_frame_sharding(r, rank, world)
         mode = "frame-sharded: every rank traces its own frame, rows accumulate on their owners"
     ok = True
     for frame in range(4):
