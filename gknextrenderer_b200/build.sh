@@ -23,6 +23,11 @@ $NVCC $ARCH -shared -o lib/libgknext_cuda.so "${objs[@]}" -lcudart
 g++ -O2 -std=c++17 -fPIC -shared -Wall -o lib/libgknext_host.so host/gk_assets.cpp host/gk_engine.cpp host/gk_host_capi.cpp \
     -pthread -Llib -lgknext_cuda -Wl,-rpath,'$ORIGIN'
 # the multi-GPU compositor over NCCL (include/gknext_compositor.h); NCCL headers/libs: the system package of this image
-g++ -O2 -std=c++17 -fPIC -shared -Wall -o lib/libgknext_comp.so host/gk_compositor.cpp -I/usr/local/cuda/include \
-    -Llib -lgknext_cuda -L/usr/local/cuda/lib64 -lcudart -lnccl -Wl,-rpath,'$ORIGIN'
+COMP="g++ -O2 -std=c++17 -fPIC -shared -Wall -o lib/libgknext_comp.so host/gk_compositor.cpp -I/usr/local/cuda/include -Llib -lgknext_cuda -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,\$ORIGIN"
+if ! $COMP -lnccl 2>/dev/null; then
+  # no system NCCL dev package: link against the one PyTorch ships (same SONAME, libnccl.so.2)
+  NCCL_DIR=$(python -c "import nvidia.nccl, os; print(os.path.dirname(nvidia.nccl.__file__))" 2>/dev/null || true)
+  if [ -z "$NCCL_DIR" ]; then NCCL_DIR=$(python -c "import os, site; print(os.path.join(site.getsitepackages()[0], 'nvidia', 'nccl'))"); fi
+  $COMP -I"$NCCL_DIR/include" "$NCCL_DIR/lib/libnccl.so.2"
+fi
 echo "built lib/libgknext_cuda.so lib/libgknext_host.so lib/libgknext_comp.so"
