@@ -339,6 +339,33 @@ def test_frame_is_deterministic_and_tiles_compose_bit_exactly(built):
         assert np.array_equal(a[p].view(np.uint8), union[p].view(np.uint8)), f"tile union differs on {p}"
 
 
+@pytest.mark.parametrize("W,H,tile_rows", [(320, 176, 16), (328, 180, 4), (317, 90, 16), (320, 180, 6)])
+def test_path_order_does_not_change_the_frame(built, W, H, tile_rows):
+    """The order in which pixels are dealt to paths (option micro_tiles: 32x1 strips, 8x4 pixel blocks per warp, 16x16 squares per
+    thread block; widths / tile heights that do not divide fall back to the coarser order) is a scheduling choice: every plane of the
+    frame must be bit-identical under all three, on a whole frame and on one rank's share of a tiled frame."""
+    eng = gk.Engine("room", 60000, 5)
+    eng.set(TAA=0, NumberOfSamples=2, NumberOfBounces=4)
+    ubo = eng.ubo(W, H)
+    nodes, n = eng.update_nodes()
+    planes = ("RADIANCE_DIFFUSE_F32", "RADIANCE_SPECULAR_F32", "PRIMARY_IDS", "PRIMARY_T", "OUTPUT_DIFFUSE", "ALBEDO", "NORMAL", "MOTION", "OBJECT_ID0", "RAY_COUNT")
+    for tiles in (1, 3):
+        r = gk.Renderer(W, H, device=0, tile_index=tiles - 1, tile_count=tiles, tile_rows=tile_rows)
+        r.upload_scene(eng.scene_desc()); r.update_instances(nodes, n); r.set_ubo(ubo)
+        ref = None
+        for order in (0, 1, 2):
+            r.set_option("micro_tiles", order)
+            r.trace_frame()
+            got = {p: r.readback(p).copy() for p in planes}
+            assert r.stats().primaryRays > 0
+            if ref is None:
+                ref = got
+                continue
+            for p in planes:
+                assert np.array_equal(ref[p].view(np.uint8), got[p].view(np.uint8)), f"{p} differs with micro_tiles={order} ({W}x{H}, {tiles} tile set(s), {tile_rows} rows)"
+        r.close()
+
+
 def test_refit_equals_rebuild_after_moving_instances(built):
     eng, r, orc, (nodes, n) = _setup("bricks", 64, 64, (3000, 42))
     rng = np.random.default_rng(5)
