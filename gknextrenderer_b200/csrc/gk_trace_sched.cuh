@@ -68,6 +68,16 @@ __device__ __forceinline__ void stackStore(uint32_t addr, uint32_t ref, uint32_t
 {
     asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+%3], %2;" ::"r"(addr), "r"(ref), "r"(key), "n"(kSmemStack * kSchedBlock * 4));
 }
+__device__ __forceinline__ void stackStoreRef(uint32_t addr, uint32_t ref) // occlusion queries: entries carry no key
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(ref));
+}
+__device__ __forceinline__ uint32_t stackLoadRef(uint32_t addr)
+{
+    uint32_t ref;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ref) : "r"(addr));
+    return ref;
+}
 __device__ __forceinline__ void stackLoad(uint32_t addr, uint32_t& ref, uint32_t& key)
 {
     asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+%3];" : "=r"(ref), "=r"(key) : "r"(addr), "n"(kSmemStack * kSchedBlock * 4));
@@ -108,6 +118,10 @@ __device__ __forceinline__ bool childTestPadded(const NodeFrame& F, const PlaneS
 //   words [0, kSmemStack)              stack references      } the lane keeps `top`, the shared-space byte address of its next
 //   words [kSmemStack, 2 kSmemStack)   stack keys            } free entry: a push is two stores and one add, "empty" is top == bottom
 //   words [2 kSmemStack, +9)           world-space ray: O, Dn, 1/Dn (read when an instance is entered or left)
+#ifndef GK_ANYHIT_UNORDERED
+#define GK_ANYHIT_UNORDERED 1
+#endif
+constexpr bool kAnyHitUnordered = GK_ANYHIT_UNORDERED != 0;
 template <bool kAnyHit, bool kStats, class RayIO>
 __device__ __forceinline__ void traverseScheduled(const SceneView& V, const RayIO& io, uint32_t count, uint32_t* __restrict__ cursor, const SchedParams prm,
                                                   uint32_t* sMem, TraversalStats* stats, SchedStats* sched)
@@ -174,6 +188,10 @@ __device__ __forceinline__ void traverseScheduled(const SceneView& V, const RayI
                 break;
             }
             top -= kEntryStride;
+            if (kAnyHit && kAnyHitUnordered) { // no distance to cull by: hit.t stays tmax until the ray is occluded, and then it is finished
+                cur = top < smemLimit ? stackLoadRef(top) : spill[(top - smemLimit) / kEntryStride].x;
+                return;
+            }
             uint32_t r, key;
             if (top < smemLimit) stackLoad(top, r, key);
             else r = spill[(top - smemLimit) / kEntryStride].x, key = spill[(top - smemLimit) / kEntryStride].y;
@@ -249,6 +267,36 @@ __device__ __forceinline__ void traverseScheduled(const SceneView& V, const RayI
                     const NodeFrame F = makeNodeFrame(hdr, o, rd);
                     const bool wide = (hdr.w >> 24) > 4u;
                     const bool anyWide = __any_sync(mN, wide); // mN = exactly the lanes inside this branch
+                    if (kAnyHit && kAnyHitUnordered) {
+                        // Occlusion query: the order in which the hit children are visited cannot change the answer, so no sort keys,
+                        // no nearest-first selection and one-word stack entries: the first hit child (slot order) continues, the others are pushed.
+                        uint32_t next = kNone;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            if (half == 1 && !anyWide) break;
+                            const bool present = half == 0 || wide;
+                            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
+                            if (present) q0 = __ldg(np + 1 + 3 * half), q1 = __ldg(np + 2 + 3 * half), q2 = __ldg(np + 3 + 3 * half);
+                            const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                float tn;
+                                const bool h = childTestPadded(F, sel, w[3 * k + 1], w[3 * k + 2], tmin, hit.t, tn) && w[3 * k] != kInvalid && present;
+                                const bool push = h && next != kNone;
+                                if (!deepAny) {
+                                    stackStoreRef(top, w[3 * k]);
+                                    top += push ? kEntryStride : 0u;
+                                } else if (push) pushDeep(w[3 * k], 0u);
+                                next = (h && next == kNone) ? w[3 * k] : next;
+                            }
+                        }
+                        if (kStats) {
+                            const unsigned long long depth = (top - bottom) / kEntryStride + 1;
+                            if (depth > local.maxStack) local.maxStack = depth;
+                        }
+                        if (next != kNone) cur = next;
+                        else popOrFinish(false);
+                    } else {
                     uint32_t bestKey[2] = {kNone, kNone}, bestRef[2] = {kNone, kNone};
                     const uint32_t keyMask = ~7u;
 #pragma unroll
@@ -299,6 +347,7 @@ __device__ __forceinline__ void traverseScheduled(const SceneView& V, const RayI
                     }
                     if (winKey != kNone) cur = winRef;
                     else popOrFinish(false);
+                    }
                 }
                 mN = __ballot_sync(full, alive && !(cur & kLeafBit));
             } while ((uint32_t)__popc(mN) >= prm.keepN);

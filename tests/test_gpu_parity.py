@@ -611,9 +611,23 @@ def test_all_traversal_kernels_give_identical_hits(built, variant, threshold, mo
     threshold = f"{variant}/{threshold}"
     rng = np.random.default_rng(3)
     eng, r, orc, _ = _setup("room", 64, 64, (60000, 5))
+    if variant == "1":
+        r.set_option("sched_min_rays", 0)  # batches and waves of every size on the scheduled kernel (by default it takes those of >= 1 M)
     rays = np.concatenate([ol.primary_rays(eng.ubo(320, 180), 320, 180), _random_rays(rng, 150000, (-9.5, 0.1, -9.5), (9.5, 3.9, 9.5))])
     _compare_hits(r, orc, rays, f"room60k threshold={threshold}")
+    # occlusion queries: the boolean must agree with the closest-hit query of the reference on the same segment
+    import torch
+    d_rays = torch.from_numpy(np.ascontiguousarray(rays, np.float32)).cuda()
+    d_ids = torch.zeros((rays.shape[0], 2), dtype=torch.int32, device="cuda")
+    r.intersect_device(d_rays.data_ptr(), rays.shape[0], 0, d_ids.data_ptr(), True)
+    r.synchronize()
+    occluded = d_ids[:, 0].cpu().numpy() != 0
+    closest = r.intersect(rays)[1][:, 1] != 0xFFFFFFFF
+    assert np.array_equal(occluded, closest), f"{int((occluded != closest).sum())} occlusion results disagree with the closest-hit query"
     eng, r, orc, _ = _setup("cornell", 160, 90, NumberOfSamples=2, NumberOfBounces=4)
+    if variant == "1":
+        r.set_option("sched_min_rays", 0)
+        r.set_option("coop_threshold", 0)
     ubo = eng.ubo(160, 90)
     r.set_ubo(ubo)
     r.trace_frame()
