@@ -143,7 +143,19 @@ def enable_peer_exchange(renderer, rank: int, world: int, group=None) -> bool:
         return False
     from . import _native as N
     if os.environ.get("GK_COMPOSITOR", "native") == "native" and dist.get_backend(group) == "nccl":
-        return enable_native(renderer, rank, world, group)
+        # every rank must take the same path: the native driver is used only if it came up on all of them
+        try:
+            ok = enable_native(renderer, rank, world, group)
+        except (OSError, RuntimeError, AttributeError) as e:  # library missing / not loadable on this box
+            print(f"[compositor] rank {rank}: lib/libgknext_comp.so unavailable ({e}); torch.distributed drives the exchange", flush=True)
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device(f"cuda:{torch.cuda.current_device()}"))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()):
+            return True
+        if ok:  # came up here but not everywhere
+            from . import comp_lib
+            comp_lib().gkc_destroy(_nativeComp.pop(_hkey(renderer)))
     dev = torch.device(f"cuda:{torch.cuda.current_device()}")
     mine = torch.frombuffer(bytearray(renderer.exchange_ipc_handles()), dtype=torch.uint8).to(dev)
     every = torch.empty(world * N.GK_EXCHANGE_IPC_BYTES, dtype=torch.uint8, device=dev)
