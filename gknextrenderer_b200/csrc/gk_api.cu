@@ -692,6 +692,8 @@ GkStatus gk_set_option(GkContext* ctx, const char* name, double value)
     }
     else if (n == "sched_refill_min") c.schedRefillMin = (uint32_t)std::min(32.0, std::max(1.0, value));
     else if (n == "sched_bias_node") c.schedBiasN = (uint32_t)std::max(0.0, value);
+    else if (n == "coop_divisor") c.coopDivisor = (uint32_t)std::max(1.0, value);
+    else if (n == "tail_divisor") c.tailDivisor = (uint32_t)std::max(1.0, value);
     else if (n == "micro_tiles") c.microTiles = (int)value;
     else if (n == "sched_min_rays") c.schedMinRays = (uint32_t)std::max(0.0, value);
     else if (n == "sched_keep_node") c.schedKeepN = (uint32_t)std::min(33.0, std::max(1.0, value));

@@ -215,6 +215,7 @@ struct Context {
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evCopyReady = nullptr, evCopyDone = nullptr;
     const void* asyncCopySrc = nullptr; // non-null while a copy may be in flight
+    uint32_t coopDivisor = 4, tailDivisor = 8; // swept on 1/1 .. 1/8 frame shares (2 / 4 gain 3-5 % on a room share, lose 25 % on Cornell); the cooperative kernel / the tail never take more than paths/divisor (options "coop_divisor", "tail_divisor")
     int microTiles = 2; // path order: 0 rows, 1 = 8 x 4 pixel blocks per warp, 2 = additionally 16 x 16 squares per thread block (option "micro_tiles")
     uint32_t refitRejectedInARow = 0, refitBackoffLeft = 0; // see updateInstancesOnDevice
     float tlasAreaAtBuild = 0.f;    // summed internal-node area of the TLAS when it was last built

@@ -1121,7 +1121,7 @@ static GkStatus traceFrameStreamed(Context& c)
         }
         const int cur = (int)(wave & 1u), nxt = cur ^ 1;
         const uint32_t sizeE = wave == 0 ? n : bound, sizeS = wave == 0 ? 0u : bound;
-        if (wave > 0 && bound <= std::min(c.streamTailPaths, n / 8u) && c.captureWave < 0 && !c.travStats) {
+        if (wave > 0 && bound <= std::min(c.streamTailPaths, n / std::max(1u, c.tailDivisor)) && c.captureWave < 0 && !c.travStats) {
             // a handful of long paths is left (dielectric primaries run to MaxNumberOfBounces): one launch walks each of them to
             // its end (trace -> shade -> trace ..., one path per lane) instead of a dozen waves of a few rays at ~65 us each
             const size_t ta = mark();
@@ -1150,7 +1150,7 @@ static GkStatus traceFrameStreamed(Context& c)
         const bool fork = sizeS && c.concurrentShadow;
         // waves below the threshold: the eight-lanes-per-ray kernel (a lone ray finishes ~4x sooner than on one lane); `bound` is
         // the size of an earlier wave, so a wave is only classed small when it certainly is
-        const bool small = wave > 0 && bound < std::min(c.coopThreshold, n / 4u); // relative too: a rank of an 8-GPU frame has 0.26 M paths in all
+        const bool small = wave > 0 && bound < std::min(c.coopThreshold, n / std::max(1u, c.coopDivisor)); // relative too: a rank of an 8-GPU frame has 0.26 M paths in all
         // waves too small to keep the persistent warps of the scheduled kernel fed (a rank's share of a multi-GPU frame, Cornell):
         // its refill/vote machinery then costs more than the divergence it removes, and the plain lane kernel is faster
         const bool mid = !small && wave > 0 && bound < c.schedMinRays && !c.travStats;

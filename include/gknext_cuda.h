@@ -266,7 +266,7 @@ GkStatus gk_get_stats(GkContext* ctx, GkFrameStats* out);
 GkStatus gk_get_bvh_info(GkContext* ctx, GkBvhInfo* out);
 /* Tuning hooks (the defaults are the measured optima; DESIGN.md lists the sweeps).  Unknown names return
  * GK_ERR_INVALID_ARGUMENT.  Names: "trace_variant" (0 while-while lane kernel + cooperative kernel, 1 persistent
- * vote-scheduled kernel), "sched_refill_min", "sched_bias_node", "sched_keep_node", "sched_keep_tri", "sched_min_rays", "micro_tiles", "coop_threshold", "primary_lane_kernel", "tail_threshold",
+ * vote-scheduled kernel), "sched_refill_min", "sched_bias_node", "sched_keep_node", "sched_keep_tri", "sched_min_rays", "micro_tiles", "coop_divisor", "tail_divisor", "coop_threshold", "primary_lane_kernel", "tail_threshold",
  * "tail_fraction", "concurrent_shadow", "wave_lookahead". */
 GkStatus gk_set_option(GkContext* ctx, const char* name, double value);
 /* Measurement aid for the roofline of the traversal kernels ("peak measured once with an L2-resident
