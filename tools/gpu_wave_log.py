@@ -10,7 +10,8 @@ scene, args, W, H, settings = WORKLOADS[name]
 eng = gk.Engine(scene, *args); eng.set(**settings)
 opts = dict(a.split("=") for a in sys.argv[2:])
 tiles = int(opts.pop("tiles", 1))  # >1: the share one rank of a tile-partitioned frame traces
-r = gk.Renderer(W, H, device=0, tile_index=0, tile_count=tiles, tile_rows=16); r.load(eng)
+rows, index = int(opts.pop("tile_rows", 16)), int(opts.pop("tile_index", 0))
+r = gk.Renderer(W, H, device=0, tile_index=index, tile_count=tiles, tile_rows=rows); r.load(eng)
 for k, v in opts.items():
     r.set_option(k, float(v))
 os.environ.pop("GK_WAVE_LOG")
