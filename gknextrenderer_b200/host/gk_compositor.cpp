@@ -116,12 +116,13 @@ int gkc_create(GkContext* ctx, int rank, int world, const void* id, size_t bytes
         return fail(-3);
     }
     // exchange planes of every rank -> CUDA IPC handles -> all-gather -> map
-    unsigned char mine[GK_EXCHANGE_IPC_BYTES];
+    unsigned char mine[GK_EXCHANGE_IPC_BYTES] = {0};
     std::vector<unsigned char> all;
     GkStatus s = gk_exchange_ipc_handles(ctx, mine, sizeof(mine));
     int ok = s == GK_OK ? 1 : 0;
     if (!ok) g_err = std::string("gk_exchange_ipc_handles: ") + gk_last_error();
-    if (ok && allGatherHost(c, mine, sizeof(mine), all) != 0) return fail(-2);
+    // a rank that failed still takes part in the collectives below, so that the others do not wait for it forever
+    if (allGatherHost(c, mine, sizeof(mine), all) != 0) return fail(-2);
     if (ok) {
         s = gk_exchange_open_peers(ctx, all.data(), (uint32_t)world);
         if (s != GK_OK) ok = 0, g_err = std::string("gk_exchange_open_peers: ") + gk_last_error();
