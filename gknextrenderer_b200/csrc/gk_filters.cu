@@ -112,13 +112,12 @@ constexpr int RW = TX + 2 * RH, RHT = TY + 2 * RH;
 // The four history taps of the three planes (twelve gathers at the motion-vector target) are issued before the weight loops so
 // that their latency overlaps the arithmetic; the 5x5 spatial estimate (needed only where a history tap is rejected) sums the
 // three planes while it forms each weight, so no weight array lives in registers.
-__global__ void __launch_bounds__(TX* TY, 4) k_reproject(const GkUniformBufferObject* __restrict__ ubo, ReprojectArgs A)
+__global__ void __launch_bounds__(TX* TY, 4) k_reproject(const __grid_constant__ GkUniformBufferObject U, ReprojectArgs A) // UBO in parameter space (constant bank), see k_shade_stream
 {
     __shared__ uint2 sSrc[3][RHT][RW];
     __shared__ float4 sNrm[RHT][RW]; // normal, unpacked once per texel (25 pixels read it); w = object id bits
     __shared__ float4 sYc[RHT][RW];  // YCoCg of the albedo texel
     __shared__ float4 sMn[RHT][TX], sMx[RHT][TX]; // horizontal 5-tap min / max of the albedo's YCoCg
-    const GkUniformBufferObject& U = *ubo;
     const int W = A.W, H = A.H;
     const int vx = (int)U.ViewportRect[0], vy = (int)U.ViewportRect[1];
     const int bx = blockIdx.x * TX + vx, by = blockIdx.y * TY + vy;
@@ -360,12 +359,11 @@ __device__ __forceinline__ c3 gt3fast(c3 v) { return mk(granTurismoFast(v.x), gr
 // recomputed with IEEE expf and the reference's exact grouping, because there single denormal quanta decide the result
 // (and where the reference's 0/0 NaNs appear).  Above that threshold the SFU error (4e-6 relative per weight) is three
 // orders below the half-precision step of the output.
-__global__ void __launch_bounds__(JX* JY) k_denoise_jbf(const GkUniformBufferObject* __restrict__ ubo, DenoiseArgs A)
+__global__ void __launch_bounds__(JX* JY) k_denoise_jbf(const __grid_constant__ GkUniformBufferObject U, DenoiseArgs A)
 {
     __shared__ float4 sDif[DHT][DW]; // diffuse + bias, w = luminance
     __shared__ float sFi[36];        // spatial weights of the 36 taps: they depend on the tap only
     __shared__ float sLf[36];        // ... and their base-2 logarithms (folded into the exponent of the luminance weight)
-    const GkUniformBufferObject& U = *ubo;
     const int W = A.W, H = A.H;
     const int vx = (int)U.ViewportRect[0], vy = (int)U.ViewportRect[1];
     const int bx = blockIdx.x * JX + vx, by = blockIdx.y * JY + vy;
@@ -504,14 +502,14 @@ static GkStatus runFilters(Context& c, bool ownedRowsOnly)
     R.tiles = ownedRowsOnly ? RowTiles{c.tileIndex, c.tileCount, c.tileRows} : RowTiles{0, 1, 1};
     const dim3 block(TX, TY), grid((c.width + TX - 1) / TX, (c.height + TY - 1) / TY);
     cudaEventRecord(e0, st);
-    k_reproject<<<grid, block, 0, st>>>(c.dUbo, R);
+    k_reproject<<<grid, block, 0, st>>>(c.ubo, R);
     cudaEventRecord(e1, st);
     DenoiseArgs D;
     D.diffuse = R.out[0], D.spec = R.out[1], D.albedo = R.out[2], D.id0 = R.id0, D.id1 = R.id1, D.out = (uint2*)P[GK_PLANE_DENOISED];
     D.W = R.W, D.H = R.H;
     D.tiles = R.tiles;
     const dim3 jblock(JX, JY), jgrid((c.width + JX - 1) / JX, (c.height + JY - 1) / JY);
-    k_denoise_jbf<<<jgrid, jblock, 0, st>>>(c.dUbo, D);
+    k_denoise_jbf<<<jgrid, jblock, 0, st>>>(c.ubo, D);
     cudaEventRecord(e2, st);
     GK_CUDA(cudaGetLastError());
     GK_CUDA(cudaStreamSynchronize(st));
@@ -542,7 +540,7 @@ GkStatus composeOwnedRows(Context& c)
         waitAsyncCopyBeforeWriting(c, bufs, 1);
     }
     const dim3 jblock(JX, JY), jgrid((c.width + JX - 1) / JX, (c.height + JY - 1) / JY);
-    k_denoise_jbf<<<jgrid, jblock, 0, st>>>(c.dUbo, D);
+    k_denoise_jbf<<<jgrid, jblock, 0, st>>>(c.ubo, D);
     GK_CUDA(cudaGetLastError());
     c.stats.launches += 1;
     c.tracedSinceFilter = false;

@@ -567,8 +567,10 @@ __device__ __forceinline__ void shadePath(const GkUniformBufferObject& U, const 
                 }
                 case PH_AFTER_SAMPLES: {
                     needAcc();
-                    accD = accD / float(samples);
-                    accS = accS / float(samples);
+                    if (samples != 1u) { // x / 1.0f == x bit for bit: the 1-spp real-time frame skips two IEEE vector divisions per path
+                        accD = accD / float(samples);
+                        accS = accS / float(samples);
+                    }
                     if (U.HasSun) { // DirectIlluminate, Shading.slang:826-845
                         needPrimary();
                         const f3 lv = mk3(U.SunDirection[0], U.SunDirection[1], U.SunDirection[2]);
@@ -658,8 +660,10 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_shade(const GkUniformBuffer
 
 // Device-driven form of the same kernel: the queue sizes are read from device memory and the blocks stride over the
 // queue, so a wave can be enqueued before the host knows how many rays the previous wave produced.
+// The 784-byte UBO travels as a kernel parameter (constant bank): ncu attributed 5 % of this kernel's stall samples to the first
+// global load of a UBO matrix; parameter space makes every U.* operand a constant-cache / uniform-register read.
 template <int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks) k_shade_stream(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, ShadeScene SS, PathState S, PlaneView PL, RayQueue inE,
+__global__ void __launch_bounds__(256, kMinBlocks) k_shade_stream(const __grid_constant__ GkUniformBufferObject U, FrameParams P, ShadeScene SS, PathState S, PlaneView PL, RayQueue inE,
                                                       RayQueue inS, RayQueue outE, RayQueue outS)
 {
     const uint32_t countE = *inE.count, countS = *inS.count, total = countE + countS;
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_shade_stream(const GkUnifor
             const bool fromExtend = i < countE;
             const uint32_t slot = fromExtend ? i : i - countE;
             path = fromExtend ? inE.path[slot] : inS.path[slot];
-            shadePath(*ubo, P, SS, S, PL, path, QueueSrc{inE, inS, slot}, e);
+            shadePath(U, P, SS, S, PL, path, QueueSrc{inE, inS, slot}, e);
         }
         appendRay(e, path, outE, outS);
     }
@@ -736,7 +740,7 @@ __global__ void __launch_bounds__(128, 4) k_tail(const GkUniformBufferObject* __
 // primaries run to MaxNumberOfBounces) whose rays depend on one another, so the launch is bound by the latency of a single
 // ray.  The cooperative traversal (lane j tests child j / triangle j) cuts that latency several times; lane 0 of a group runs
 // the path's state machine and hands the next ray to its group through shuffles.
-__global__ void __launch_bounds__(256, 2) k_tail_coop(const GkUniformBufferObject* __restrict__ ubo, FrameParams P, SceneView V, ShadeScene SS, PathState S, PlaneView PL,
+__global__ void __launch_bounds__(256, 2) k_tail_coop(const __grid_constant__ GkUniformBufferObject U, FrameParams P, SceneView V, ShadeScene SS, PathState S, PlaneView PL,
                                                       RayQueue inE, RayQueue inS, unsigned long long* __restrict__ counters)
 {
     __shared__ uint2 stack[kRaysPerBlock * kStackStride];
@@ -769,7 +773,7 @@ __global__ void __launch_bounds__(256, 2) k_tail_coop(const GkUniformBufferObjec
                 r.tuvp = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
                 r.inst = h.inst;
                 r.occ = hit;
-                shadePath(*ubo, P, SS, S, PL, path, r, e);
+                shadePath(U, P, SS, S, PL, path, r, e);
             }
             const int src = (int)shift; // lane 0 of the group
             kind = __shfl_sync(gmask, e.kind, src);
@@ -1126,7 +1130,7 @@ static GkStatus traceFrameStreamed(Context& c)
             // its end (trace -> shade -> trace ..., one path per lane) instead of a dozen waves of a few rays at ~65 us each
             const size_t ta = mark();
             GK_CUDA(cudaMemsetAsync(c.dTailCounters, 0, 3 * sizeof(unsigned long long), st));
-            if (c.tailCoop) k_tail_coop<<<gridFor((size_t)2 * bound * 8, 256), 256, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.dTailCounters);
+            if (c.tailCoop) k_tail_coop<<<gridFor((size_t)2 * bound * 8, 256), 256, 0, st>>>(c.ubo, P, V, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.dTailCounters);
             else k_tail<<<gridFor((size_t)2 * bound, 128), 128, 0, st>>>(c.dUbo, P, V, SS, c.paths, PL, c.extendQ[cur], 0, c.shadowQ[cur], 0, c.dTailCounters, 1);
             fs.launches++;
             const size_t tb = mark();
@@ -1192,9 +1196,9 @@ static GkStatus traceFrameStreamed(Context& c)
         GK_CUDA(cudaMemsetAsync(c.extendQ[nxt].count, 0, sizeof(uint32_t), st));
         GK_CUDA(cudaMemsetAsync(c.shadowQ[nxt].count, 0, sizeof(uint32_t), st));
         const unsigned shadeGrid = std::max(1u, std::min((unsigned)(c.smCount * shadeBlocksPerSm * 2), (unsigned)gridFor((size_t)sizeE + sizeS)));
-        if (shadeBlocksPerSm == 4) k_shade_stream<4><<<shadeGrid, 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
-        else if (shadeBlocksPerSm == 3) k_shade_stream<3><<<shadeGrid, 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
-        else k_shade_stream<2><<<shadeGrid, 256, 0, st>>>(c.dUbo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
+        if (shadeBlocksPerSm == 4) k_shade_stream<4><<<shadeGrid, 256, 0, st>>>(c.ubo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
+        else if (shadeBlocksPerSm == 3) k_shade_stream<3><<<shadeGrid, 256, 0, st>>>(c.ubo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
+        else k_shade_stream<2><<<shadeGrid, 256, 0, st>>>(c.ubo, P, SS, c.paths, PL, c.extendQ[cur], c.shadowQ[cur], c.extendQ[nxt], c.shadowQ[nxt]);
         const size_t f = mark();
         k_wave_end<<<1, 1, 0, st>>>(c.extendQ[nxt].count, c.shadowQ[nxt].count, c.dWave + 4 * (size_t)wave, tag);
         fs.launches += 2;
