@@ -149,7 +149,7 @@ def test_golden_tinybvh_vectors_on_gpu(built):
         g = np.load(os.path.join(os.path.dirname(__file__), "golden", fixture))
         eng, r, orc, _ = _setup(scene, 64, 64, args)
         o_tuv, o_ids = orc.intersect(g["rays"])
-        assert np.array_equal(o_ids, g["ids"]), f"{fixture}: the host-side scene differs from the one the fixture was generated from (different libm?): regenerate with tools/make_golden.py"
+        assert np.array_equal(o_ids, g["ids"]), f"{fixture}: the host-side scene differs from the one the fixture was generated from (different libm?): regenerate with tests/tools/make_golden.py"
         tuv, ids = r.intersect(g["rays"])
         differ, exact, eps, hard = _classify(tuv, ids, g["tuv"], g["ids"], f"golden {fixture}")
         assert hard.sum() == 0 and differ.sum() <= 2e-3 * len(ids)

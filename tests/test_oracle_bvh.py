@@ -1,5 +1,5 @@
 """Pins the oracle's BVH restatement (oracle/orc_bvh.cpp):
-  1. against the committed golden vectors produced by the REAL tinybvh (tools/make_golden.py),
+  1. against the committed golden vectors produced by the REAL tinybvh (tests/tools/make_golden.py),
   2. against the real tinybvh itself (oracle/_ref) when that library is present, bit for bit,
      including the built trees node by node,
   3. against a brute-force closest hit that uses no BVH at all.

@@ -1,6 +1,6 @@
 """Classifies hit mismatches between the CUDA traversal, the oracle BVH and brute force."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import gknextrenderer_b200 as gk

@@ -1,7 +1,7 @@
 """Dumps the rays whose GPU hit differs from the real tinybvh's (ids or distance) for offline analysis.
     python tools/gpu_dump_mismatches.py bricks out.npz"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import gknextrenderer_b200 as gk, oracle_lib as ol

@@ -1,13 +1,13 @@
 """Generates tests/golden/*.npz by running the REAL tinybvh (oracle/_ref, compiled from
 /root/reference/src/ThirdParty/tinybvh/tiny_bvh.h) on rays of the built-in scenes.
-Run in the build container (the reference tree must be present):  python tools/make_golden.py
+Run in the build container (the reference tree must be present):  python tests/tools/make_golden.py
 The fixtures pin oracle/orc_bvh.cpp wherever the reference tree is absent (e.g. the GPU box)."""
 import ctypes as C
 import hashlib
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
